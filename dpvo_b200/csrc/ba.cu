@@ -1,0 +1,726 @@
+// fastba: in-place Gauss-Newton bundle adjustment over the patch graph, sm_100a.
+//
+// Replaces dpvo/fastba/ba_cuda.cu:232-376 (per-edge kernel with ~340 global float atomics per
+// edge), the ~30 ATen launches per iteration around it (:484-563, dense E, matmuls, cuSOLVER
+// potrf/potrs on a 60x60 system) and the retraction kernels (:178-229) with TWO launches per
+// Gauss-Newton iteration and no float atomics:
+//
+//   ba_reduce_kernel  one warp per work item, warp-shuffle reductions only
+//       * pair items  (edges sharing (i,j), from the ij grouping): sum of the 6x6 pose blocks
+//                     JiJi^T, JiJj^T, JjJj^T and the pose gradients -> one 90-float record
+//       * patch items (edges sharing a patch, from the kk grouping): C_k, u_k and the dense row
+//                     E_k (6N) of the pose/depth coupling -> global
+//   ba_solve_kernel   one 8-CTA thread-block cluster
+//       * each CTA forms its share of the Schur products  sum_k Q_k E_k E_k^T, sum_k Q_k u_k E_k
+//       * partials are reduced over distributed shared memory in a fixed order
+//       * CTA 0 assembles B from the pair records, applies the damping, Cholesky-factors and
+//         solves the 6N x 6N system in shared memory, retracts the poses
+//       * all CTAs back-substitute the depth updates and retract the patches
+// Results are bit-reproducible run to run (the reference's are not: unordered atomics).
+#include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace dpvo {
+
+constexpr int BA_MAX_N = 32;          // free poses held on chip
+constexpr int BA_REC = 90;            // floats per pair record
+constexpr int BA_CLUSTER = 8;
+constexpr int BA_SOLVE_THREADS = 512;
+constexpr int BA_MAX_FRAMES = 96;     // frame span of the pair lookup table
+
+struct GroupHeaderBA {                // mirror of graph.cu:GroupHeader (ranges of the ij grouping)
+  unsigned barrier; int npass[3];
+  long long amin, amax, bmin, bmax, smin, smax;
+};
+
+struct BaArgs {
+  float* poses; float* patches; const float* intrinsics;
+  const float* target; const float* weight; const float* lmbda;
+  const int64_t* ii; const int64_t* jj; const int64_t* kk;
+  int64_t E; int P; int t0; int N;     // N = t1 - t0 free poses
+  // kk grouping (patches)
+  const int32_t* k_order; const int32_t* k_start; const int64_t* k_key; const int32_t* k_n;
+  // ij grouping (pose pairs)
+  const int32_t* p_order; const int32_t* p_start; const int64_t* p_key_i; const int64_t* p_key_j;
+  const int32_t* p_n; const GroupHeaderBA* p_hdr;
+  // scratch
+  float* Ed;      // [M][6N]
+  float* Qk;      // [M]   1/(C+lambda)
+  float* uk;      // [M]
+  float* rec;     // [Gp][90]
+  float* dX;      // [6N]
+};
+
+// ---- Eigen-free SE3 helpers, same formulas as ba_cuda.cu:36-174 -------------------------
+__device__ __forceinline__ void actSO3(const float* q, const float* X, float* Y) {
+  float uv[3];
+  uv[0] = 2.0f * (q[1] * X[2] - q[2] * X[1]);
+  uv[1] = 2.0f * (q[2] * X[0] - q[0] * X[2]);
+  uv[2] = 2.0f * (q[0] * X[1] - q[1] * X[0]);
+  Y[0] = X[0] + q[3] * uv[0] + (q[1] * uv[2] - q[2] * uv[1]);
+  Y[1] = X[1] + q[3] * uv[1] + (q[2] * uv[0] - q[0] * uv[2]);
+  Y[2] = X[2] + q[3] * uv[2] + (q[0] * uv[1] - q[1] * uv[0]);
+}
+__device__ __forceinline__ void relSE3(const float* ti, const float* qi, const float* tj, const float* qj,
+                                       float* tij, float* qij) {
+  qij[0] = -qj[3] * qi[0] + qj[0] * qi[3] - qj[1] * qi[2] + qj[2] * qi[1];
+  qij[1] = -qj[3] * qi[1] + qj[1] * qi[3] - qj[2] * qi[0] + qj[0] * qi[2];
+  qij[2] = -qj[3] * qi[2] + qj[2] * qi[3] - qj[0] * qi[1] + qj[1] * qi[0];
+  qij[3] = qj[3] * qi[3] + qj[0] * qi[0] + qj[1] * qi[1] + qj[2] * qi[2];
+  actSO3(qij, ti, tij);
+  tij[0] = tj[0] - tij[0]; tij[1] = tj[1] - tij[1]; tij[2] = tj[2] - tij[2];
+}
+// Y = Adj(T)^T X for T = (t, q)   (ba_cuda.cu:57-72)
+__device__ __forceinline__ void adjSE3(const float* t, const float* q, const float* X, float* Y) {
+  const float qinv[4] = {-q[0], -q[1], -q[2], q[3]};
+  actSO3(qinv, &X[0], &Y[0]);
+  actSO3(qinv, &X[3], &Y[3]);
+  float u[3], v[3];
+  u[0] = t[2] * X[1] - t[1] * X[2];
+  u[1] = t[0] * X[2] - t[2] * X[0];
+  u[2] = t[1] * X[0] - t[0] * X[1];
+  actSO3(qinv, u, v);
+  Y[3] += v[0]; Y[4] += v[1]; Y[5] += v[2];
+}
+__device__ __forceinline__ void expSO3(const float* phi, float* q) {
+  const float theta_sq = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+  const float theta_p4 = theta_sq * theta_sq;
+  const float theta = sqrtf(theta_sq);
+  float imag, real;
+  if (theta_sq < 1e-8f) {
+    imag = 0.5f - (1.0f / 48.0f) * theta_sq + (1.0f / 3840.0f) * theta_p4;
+    real = 1.0f - (1.0f / 8.0f) * theta_sq + (1.0f / 384.0f) * theta_p4;
+  } else {
+    imag = sinf(0.5f * theta) / theta;
+    real = cosf(0.5f * theta);
+  }
+  q[0] = imag * phi[0]; q[1] = imag * phi[1]; q[2] = imag * phi[2]; q[3] = real;
+}
+__device__ __forceinline__ void crossInplace(const float* a, float* b) {
+  const float x[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+  b[0] = x[0]; b[1] = x[1]; b[2] = x[2];
+}
+__device__ __forceinline__ void expSE3(const float* xi, float* t, float* q) {
+  expSO3(xi + 3, q);
+  float tau[3] = {xi[0], xi[1], xi[2]};
+  const float phi[3] = {xi[3], xi[4], xi[5]};
+  const float theta_sq = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+  const float theta = sqrtf(theta_sq);
+  t[0] = tau[0]; t[1] = tau[1]; t[2] = tau[2];
+  if (theta > 1e-4f) {
+    const float a = (1.0f - cosf(theta)) / theta_sq;
+    crossInplace(phi, tau);
+    t[0] += a * tau[0]; t[1] += a * tau[1]; t[2] += a * tau[2];
+    const float b = (theta - sinf(theta)) / (theta * theta_sq);
+    crossInplace(phi, tau);
+    t[0] += b * tau[0]; t[1] += b * tau[1]; t[2] += b * tau[2];
+  }
+}
+// pose <- Exp(xi) * pose   (ba_cuda.cu:156-174)
+__device__ __forceinline__ void retrSE3(const float* xi, const float* t, const float* q, float* t1, float* q1) {
+  float dt[3] = {0, 0, 0};
+  float dq[4] = {0, 0, 0, 1};
+  expSE3(xi, dt, dq);
+  q1[0] = dq[3] * q[0] + dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1];
+  q1[1] = dq[3] * q[1] + dq[1] * q[3] + dq[2] * q[0] - dq[0] * q[2];
+  q1[2] = dq[3] * q[2] + dq[2] * q[3] + dq[0] * q[1] - dq[1] * q[0];
+  q1[3] = dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2];
+  actSO3(dq, t, t1);
+  t1[0] += dt[0]; t1[1] += dt[1]; t1[2] += dt[2];
+}
+
+// ---- linearisation of one edge: both residual rows (ba_cuda.cu:265-333) ------------------
+struct EdgeLin {
+  float w[2], r[2], Jz[2];
+  float Ji[2][6];   // Adj^T Jj, as in the reference (enters with a minus sign)
+  float Jj[2][6];
+};
+
+__device__ __forceinline__ void linearize_edge(const BaArgs& a, int64_t e, float fx, float fy, float cx, float cy,
+                                               EdgeLin& L) {
+  const int64_t ix = a.ii[e], jx = a.jj[e], kx = a.kk[e];
+  const float* pi = a.poses + ix * 7;
+  const float* pj = a.poses + jx * 7;
+  const float ti[3] = {pi[0], pi[1], pi[2]}, qi[4] = {pi[3], pi[4], pi[5], pi[6]};
+  const float tj[3] = {pj[0], pj[1], pj[2]}, qj[4] = {pj[3], pj[4], pj[5], pj[6]};
+  const int P = a.P, c = P / 2;
+  const float* pk = a.patches + kx * 3 * P * P + c * P + c;
+  float Xi[4], Xj[4];
+  Xi[0] = (pk[0] - cx) / fx;
+  Xi[1] = (pk[P * P] - cy) / fy;
+  Xi[2] = 1.0f;
+  Xi[3] = pk[2 * P * P];
+  float tij[3], qij[4];
+  relSE3(ti, qi, tj, qj, tij, qij);
+  actSO3(qij, Xi, Xj);
+  Xj[3] = Xi[3];
+  Xj[0] += Xi[3] * tij[0]; Xj[1] += Xi[3] * tij[1]; Xj[2] += Xi[3] * tij[2];
+  const float X = Xj[0], Y = Xj[1], Z = Xj[2], W = Xj[3];
+  const float d = ((double)Z >= 0.2) ? 1.0f / Z : 0.0f;
+  const float d2 = d * d;
+  const float x1 = fx * (X / Z) + cx;
+  const float y1 = fy * (Y / Z) + cy;
+  const float rx = a.target[e * 2 + 0] - x1;
+  const float ry = a.target[e * 2 + 1] - y1;
+  const bool in_bounds = (sqrtf(rx * rx + ry * ry) < 128.0f) && ((double)Z > 0.2) && (x1 > -64.0f) &&
+                         (y1 > -64.0f) && (x1 < 2.0f * cx + 64.0f) && (y1 < 2.0f * cy + 64.0f);
+  const float mask = in_bounds ? 1.0f : 0.0f;
+  L.r[0] = rx; L.r[1] = ry;
+  L.w[0] = mask * a.weight[e * 2 + 0];
+  L.w[1] = mask * a.weight[e * 2 + 1];
+  L.Jz[0] = fx * (tij[0] * d - tij[2] * (X * d2));
+  L.Jz[1] = fy * (tij[1] * d - tij[2] * (Y * d2));
+  L.Jj[0][0] = fx * W * d; L.Jj[0][1] = 0.0f; L.Jj[0][2] = fx * -X * W * d2;
+  L.Jj[0][3] = fx * -X * Y * d2; L.Jj[0][4] = fx * (1.0f + X * X * d2); L.Jj[0][5] = fx * -Y * d;
+  L.Jj[1][0] = 0.0f; L.Jj[1][1] = fy * W * d; L.Jj[1][2] = fy * -Y * W * d2;
+  L.Jj[1][3] = fy * (-1.0f - Y * Y * d2); L.Jj[1][4] = fy * (X * Y * d2); L.Jj[1][5] = fy * X * d;
+  adjSE3(tij, qij, L.Jj[0], L.Ji[0]);
+  adjSE3(tij, qij, L.Jj[1], L.Ji[1]);
+}
+
+// ==========================================================================================
+// kernel A: per-pair and per-patch reductions
+// ==========================================================================================
+constexpr int BA_RED_WARPS = 4;
+
+__global__ void __launch_bounds__(BA_RED_WARPS * 32)
+ba_reduce_kernel(const BaArgs a) {
+  __shared__ float ek_all[BA_RED_WARPS][6 * BA_MAX_N];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* ek = ek_all[wib];
+  const float fx = a.intrinsics[0], fy = a.intrinsics[1], cx = a.intrinsics[2], cy = a.intrinsics[3];
+  const float lm = a.lmbda[0];
+  const int Gk = *a.k_n, Gp = (a.N > 0) ? *a.p_n : 0;
+  const int N = a.N, N6 = 6 * a.N;
+  const int nwarps = gridDim.x * BA_RED_WARPS;
+
+  for (int item = blockIdx.x * BA_RED_WARPS + wib; item < Gk + Gp; item += nwarps) {
+    if (item < Gk) {
+      // ------------------------------------------------------------ patch item
+      const int g = item;
+      const int gs = a.k_start[g], ge = a.k_start[g + 1];
+      for (int i = lane; i < N6; i += 32) ek[i] = 0.0f;
+      __syncwarp();
+      float Csum = 0.0f, usum = 0.0f;
+      for (int base = gs; base < ge; base += 32) {
+        const bool act = base + lane < ge;
+        float c = 0.f, u = 0.f, Ei[6] = {0, 0, 0, 0, 0, 0}, Ej[6] = {0, 0, 0, 0, 0, 0};
+        int ix = -1, jx = -1;
+        if (act) {
+          const int64_t e = a.k_order[base + lane];
+          EdgeLin L;
+          linearize_edge(a, e, fx, fy, cx, cy, L);
+          ix = (int)(a.ii[e] - a.t0); jx = (int)(a.jj[e] - a.t0);
+          if (ix < 0 || ix >= N) ix = -1;
+          if (jx < 0 || jx >= N) jx = -1;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            c += L.w[r] * L.Jz[r] * L.Jz[r];
+            u += L.w[r] * L.r[r] * L.Jz[r];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+              Ei[k] += -L.w[r] * L.Jz[r] * L.Ji[r][k];
+              Ej[k] += L.w[r] * L.Jz[r] * L.Jj[r][k];
+            }
+          }
+        }
+        Csum += warp_sum(c);
+        usum += warp_sum(u);
+        if (N > 0) {
+          // source-pose block: all edges of a patch normally share ix -> one shuffle reduction
+          const int ix0 = __shfl_sync(0xffffffffu, ix, 0);
+          const bool same_i = __all_sync(0xffffffffu, !act || ix == ix0);
+          const unsigned dup = __match_any_sync(0xffffffffu, act ? jx : -2 - lane);
+          const bool uniq_j = __all_sync(0xffffffffu, !act || jx < 0 || __popc(dup) == 1);
+          if (same_i) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+              const float s = warp_sum(Ei[k]);
+              if (lane == 0 && ix0 >= 0) ek[6 * ix0 + k] += s;
+            }
+          }
+          __syncwarp();
+          if (uniq_j) {
+            if (act && jx >= 0) {
+#pragma unroll
+              for (int k = 0; k < 6; ++k) ek[6 * jx + k] += Ej[k];
+            }
+          }
+          __syncwarp();
+          if (!same_i || !uniq_j) {
+            // general graphs: ordered, lane-serial accumulation (still deterministic)
+            for (int l = 0; l < 32; ++l) {
+              if (lane == l && act) {
+                if (!same_i && ix >= 0) for (int k = 0; k < 6; ++k) ek[6 * ix + k] += Ei[k];
+                if (!uniq_j && jx >= 0) for (int k = 0; k < 6; ++k) ek[6 * jx + k] += Ej[k];
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < N6; i += 32) a.Ed[(int64_t)g * N6 + i] = ek[i];
+      if (lane == 0) { a.Qk[g] = 1.0f / (Csum + lm); a.uk[g] = usum; }
+      __syncwarp();
+    } else {
+      // ------------------------------------------------------------ pair item
+      const int p = item - Gk;
+      const int gs = a.p_start[p], ge = a.p_start[p + 1];
+      float acc[BA_REC];
+#pragma unroll
+      for (int k = 0; k < BA_REC; ++k) acc[k] = 0.0f;
+      for (int idx = gs + lane; idx < ge; idx += 32) {
+        EdgeLin L;
+        linearize_edge(a, a.p_order[idx], fx, fy, cx, cy, L);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float w = L.w[r];
+          int o = 0;
+#pragma unroll
+          for (int x = 0; x < 6; ++x)
+#pragma unroll
+            for (int y = x; y < 6; ++y) acc[o++] += w * L.Ji[r][x] * L.Ji[r][y];
+#pragma unroll
+          for (int x = 0; x < 6; ++x)
+#pragma unroll
+            for (int y = 0; y < 6; ++y) acc[o++] += -w * L.Ji[r][x] * L.Jj[r][y];
+#pragma unroll
+          for (int x = 0; x < 6; ++x)
+#pragma unroll
+            for (int y = x; y < 6; ++y) acc[o++] += w * L.Jj[r][x] * L.Jj[r][y];
+#pragma unroll
+          for (int x = 0; x < 6; ++x) acc[o++] += -w * L.r[r] * L.Ji[r][x];
+#pragma unroll
+          for (int x = 0; x < 6; ++x) acc[o++] += w * L.r[r] * L.Jj[r][x];
+        }
+      }
+      float mine[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < BA_REC; ++k) {
+        const float s = warp_sum(acc[k]);
+        if ((k & 31) == lane) mine[k >> 5] = s;
+      }
+      float* rp = a.rec + (int64_t)p * BA_REC;
+      rp[lane] = mine[0];
+      rp[32 + lane] = mine[1];
+      if (64 + lane < BA_REC) rp[64 + lane] = mine[2];
+    }
+  }
+}
+
+// ==========================================================================================
+// kernel B: Schur complement, solve, retraction -- one thread-block cluster
+// ==========================================================================================
+__device__ __forceinline__ int tri_index(int x, int y) {   // upper triangle of a 6x6 block, x <= y
+  return x * 6 - (x * (x - 1)) / 2 + (y - x);
+}
+
+struct SolveSmem {
+  float S[6 * BA_MAX_N][6 * BA_MAX_N + 1];   // Schur partial, then the full system (CTA 0)
+  float y[6 * BA_MAX_N];
+  float dx[6 * BA_MAX_N];
+  float Et[32][6 * BA_MAX_N + 1];            // tile of E rows
+  float Qt[32], Ut[32];
+  int lut[BA_MAX_FRAMES * BA_MAX_FRAMES];    // (frame_i - fmin, frame_j - fmin) -> pair id + 1
+};
+
+__global__ void __cluster_dims__(BA_CLUSTER, 1, 1) __launch_bounds__(BA_SOLVE_THREADS, 1)
+ba_solve_kernel(const BaArgs a) {
+  extern __shared__ __align__(16) unsigned char solve_smem_raw[];
+  SolveSmem& sm = *reinterpret_cast<SolveSmem*>(solve_smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  const int N = a.N, N6 = 6 * N;
+  const int Gk = *a.k_n;
+  const int P = a.P;
+
+  // patches of this CTA: contiguous slice [m0, m1)
+  const int per = (Gk + BA_CLUSTER - 1) / BA_CLUSTER;
+  const int m0 = min(Gk, rank * per), m1 = min(Gk, m0 + per);
+
+  if (N > 0) {
+    // ---- 1. partial Schur products over this CTA's patches (upper triangle + rhs column)
+    for (int o = tid; o < N6 * N6; o += BA_SOLVE_THREADS) sm.S[o / N6][o % N6] = 0.0f;
+    for (int i = tid; i < N6; i += BA_SOLVE_THREADS) sm.y[i] = 0.0f;
+    __syncthreads();
+    for (int mbase = m0; mbase < m1; mbase += 32) {
+      const int cnt = min(32, m1 - mbase);
+      for (int i = tid; i < cnt * N6; i += BA_SOLVE_THREADS) {
+        const int r = i / N6, c = i - r * N6;
+        sm.Et[r][c] = a.Ed[(int64_t)(mbase + r) * N6 + c];
+      }
+      if (tid < cnt) { sm.Qt[tid] = a.Qk[mbase + tid]; sm.Ut[tid] = a.uk[mbase + tid]; }
+      __syncthreads();
+      // every thread owns fixed (row, col) entries, so no atomics are needed
+      for (int o = tid; o < N6 * N6 + N6; o += BA_SOLVE_THREADS) {
+        if (o < N6 * N6) {
+          const int row = o / N6, col = o - row * N6;
+          if (row > col) continue;
+          float s = 0.0f;
+          for (int k = 0; k < cnt; ++k) s += sm.Qt[k] * sm.Et[k][row] * sm.Et[k][col];
+          sm.S[row][col] += s;
+        } else {
+          const int row = o - N6 * N6;
+          float s = 0.0f;
+          for (int k = 0; k < cnt; ++k) s += sm.Qt[k] * sm.Ut[k] * sm.Et[k][row];
+          sm.y[row] += s;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  cluster.sync();
+
+  if (N > 0 && rank == 0) {
+    // ---- 2. fixed-order reduction of the partials over distributed shared memory
+    for (int o = tid; o < N6 * N6 + N6; o += BA_SOLVE_THREADS) {
+      if (o < N6 * N6) {
+        const int row = o / N6, col = o - row * N6;
+        if (row <= col) {
+          float s = sm.S[row][col];
+          for (int r = 1; r < BA_CLUSTER; ++r) {
+            const SolveSmem* peer = cluster.map_shared_rank(&sm, r);
+            s += peer->S[row][col];
+          }
+          sm.S[row][col] = s;
+        }
+      } else {
+        const int row = o - N6 * N6;
+        float s = sm.y[row];
+        for (int r = 1; r < BA_CLUSTER; ++r) {
+          const SolveSmem* peer = cluster.map_shared_rank(&sm, r);
+          s += peer->y[row];
+        }
+        sm.y[row] = s;
+      }
+    }
+  }
+  cluster.sync();   // peers may now reuse their shared memory
+
+  if (N > 0 && rank == 0) {
+    // ---- 3. assemble  S = B - E Q E^T,  y = v - E Q u  from the pair records
+    const int Gp = *a.p_n;
+    const long long fmin = min(a.p_hdr->amin, a.p_hdr->bmin);
+    const long long fmax = max(a.p_hdr->amax, a.p_hdr->bmax);
+    const long long span = fmax - fmin + 1;
+    const bool use_lut = span <= BA_MAX_FRAMES;
+    const int NF = use_lut ? (int)span : 0;
+    for (int i = tid; i < NF * NF; i += BA_SOLVE_THREADS) sm.lut[i] = 0;
+    __syncthreads();
+    if (use_lut)
+      for (int p = tid; p < Gp; p += BA_SOLVE_THREADS)
+        sm.lut[(int)(a.p_key_i[p] - fmin) * NF + (int)(a.p_key_j[p] - fmin)] = p + 1;
+    __syncthreads();
+    const int foff = (int)(a.t0 - fmin);   // frame index of free pose 0 inside the lut (may be < 0)
+    for (int o = tid; o < N6 * N6 + N6; o += BA_SOLVE_THREADS) {
+      if (o < N6 * N6) {
+        const int row = o / N6, col = o - row * N6;
+        if (row > col) continue;
+        const int bi = row / 6, x = row - 6 * bi, bj = col / 6, yy = col - 6 * bj;
+        float b = 0.0f;
+        if (use_lut) {
+          const int fi = bi + foff, fj = bj + foff;
+          if (bi != bj) {
+            if (fi >= 0 && fi < NF && fj >= 0 && fj < NF) {
+              const int p1 = sm.lut[fi * NF + fj], p2 = sm.lut[fj * NF + fi];
+              if (p1) b += a.rec[(int64_t)(p1 - 1) * BA_REC + 21 + x * 6 + yy];
+              if (p2) b += a.rec[(int64_t)(p2 - 1) * BA_REC + 21 + yy * 6 + x];
+            }
+          } else if (fi >= 0 && fi < NF) {
+            const int t = tri_index(x, yy);
+            for (int f = 0; f < NF; ++f) {
+              const int p1 = sm.lut[fi * NF + f];     // edges leaving frame fi: Ji Ji^T
+              if (p1) {
+                b += a.rec[(int64_t)(p1 - 1) * BA_REC + t];
+                if (f == fi) b += a.rec[(int64_t)(p1 - 1) * BA_REC + 21 + x * 6 + yy] +
+                                  a.rec[(int64_t)(p1 - 1) * BA_REC + 21 + yy * 6 + x];
+              }
+              const int p2 = sm.lut[f * NF + fi];     // edges arriving in frame fi: Jj Jj^T
+              if (p2) b += a.rec[(int64_t)(p2 - 1) * BA_REC + 57 + t];
+            }
+          }
+        } else {
+          // wide frame span (long-range edges): scan the pair list, still in a fixed order
+          const long long Fi = a.t0 + bi, Fj = a.t0 + bj;
+          const int t = tri_index(x, yy);
+          for (int p = 0; p < Gp; ++p) {
+            const long long pi = a.p_key_i[p], pj = a.p_key_j[p];
+            const float* rp = a.rec + (int64_t)p * BA_REC;
+            if (bi != bj) {
+              if (pi == Fi && pj == Fj) b += rp[21 + x * 6 + yy];
+              if (pi == Fj && pj == Fi) b += rp[21 + yy * 6 + x];
+            } else {
+              if (pi == Fi) { b += rp[t]; if (pj == Fi) b += rp[21 + x * 6 + yy] + rp[21 + yy * 6 + x]; }
+              if (pj == Fi) b += rp[57 + t];
+            }
+          }
+        }
+        float s = b - sm.S[row][col];
+        if (row == col) s += 1e-4f * s + 1.0f;      // S += I * (1e-4 * S + 1)   ba_cuda.cu:560
+        sm.S[row][col] = s;
+        sm.S[col][row] = s;
+      } else {
+        const int row = o - N6 * N6;
+        const int bi = row / 6, x = row - 6 * bi;
+        float v = 0.0f;
+        if (use_lut) {
+          const int fi = bi + foff;
+          if (fi >= 0 && fi < NF) {
+            for (int f = 0; f < NF; ++f) {
+              const int p1 = sm.lut[fi * NF + f];
+              if (p1) v += a.rec[(int64_t)(p1 - 1) * BA_REC + 78 + x];
+              const int p2 = sm.lut[f * NF + fi];
+              if (p2) v += a.rec[(int64_t)(p2 - 1) * BA_REC + 84 + x];
+            }
+          }
+        } else {
+          const long long Fi = a.t0 + bi;
+          for (int p = 0; p < Gp; ++p) {
+            if (a.p_key_i[p] == Fi) v += a.rec[(int64_t)p * BA_REC + 78 + x];
+            if (a.p_key_j[p] == Fi) v += a.rec[(int64_t)p * BA_REC + 84 + x];
+          }
+        }
+        sm.y[row] = v - sm.y[row];
+      }
+    }
+    __syncthreads();
+
+    // ---- 4. Cholesky S = L L^T in place (lower triangle), column by column
+    for (int k = 0; k < N6; ++k) {
+      if (tid == 0) sm.S[k][k] = sqrtf(sm.S[k][k]);
+      __syncthreads();
+      const float dk = sm.S[k][k];
+      for (int i = k + 1 + tid; i < N6; i += BA_SOLVE_THREADS) sm.S[i][k] /= dk;
+      __syncthreads();
+      const int rem = N6 - k - 1;
+      for (int o = tid; o < rem * rem; o += BA_SOLVE_THREADS) {
+        const int i = k + 1 + o / rem, j = k + 1 + o % rem;
+        if (j <= i) sm.S[i][j] -= sm.S[i][k] * sm.S[j][k];
+      }
+      __syncthreads();
+    }
+    // ---- 5. solve L z = y, L^T x = z with one warp (rows lane, lane+32, ...)
+    if (tid < 32) {
+      for (int k = 0; k < N6; ++k) {
+        float zk = 0.0f;
+        if (tid == (k & 31)) { zk = sm.y[k] / sm.S[k][k]; sm.y[k] = zk; }
+        zk = __shfl_sync(0xffffffffu, zk, k & 31);
+        for (int i = tid; i < N6; i += 32) if (i > k) sm.y[i] -= sm.S[i][k] * zk;
+        __syncwarp();
+      }
+      for (int k = N6 - 1; k >= 0; --k) {
+        float xk = 0.0f;
+        if (tid == (k & 31)) { xk = sm.y[k] / sm.S[k][k]; sm.dx[k] = xk; }
+        xk = __shfl_sync(0xffffffffu, xk, k & 31);
+        for (int i = tid; i < N6; i += 32) if (i < k) sm.y[i] -= sm.S[k][i] * xk;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < N6; i += BA_SOLVE_THREADS) a.dX[i] = sm.dx[i];
+  }
+  cluster.sync();
+
+  // ---- 6. depth back-substitution dZ = Q (u - E^T dX) and patch retraction (ba_cuda.cu:209-229)
+  const float* dxs = nullptr;
+  if (N > 0) {
+    const SolveSmem* root = cluster.map_shared_rank(&sm, 0);
+    for (int i = tid; i < N6; i += BA_SOLVE_THREADS) sm.y[i] = root->dx[i];
+    dxs = sm.y;
+  }
+  __syncthreads();
+  for (int g = m0 + tid; g < m1; g += BA_SOLVE_THREADS) {
+    float s = a.uk[g];
+    if (N > 0) {
+      const float* er = a.Ed + (int64_t)g * N6;
+      float dot = 0.0f;
+      for (int k = 0; k < N6; ++k) dot += er[k] * dxs[k];
+      s -= dot;
+    }
+    const float dz = a.Qk[g] * s;
+    float* pd = a.patches + (a.k_key[g] * 3 + 2) * P * P;
+    float d = pd[0] + dz;
+    d = (d > 20.0f) ? 1.0f : d;
+    d = fmaxf(d, 1e-4f);
+    for (int i = 0; i < P * P; ++i) pd[i] = d;
+  }
+  // ---- 7. pose retraction (ba_cuda.cu:178-206), after every CTA is done reading dx
+  cluster.sync();
+  if (N > 0 && rank == 0 && tid < N) {
+    float* pp = a.poses + (int64_t)(a.t0 + tid) * 7;
+    const float t[3] = {pp[0], pp[1], pp[2]}, q[4] = {pp[3], pp[4], pp[5], pp[6]};
+    float xi[6];
+    for (int k = 0; k < 6; ++k) xi[k] = sm.dx[6 * tid + k];
+    float t1[3], q1[4];
+    retrSE3(xi, t, q, t1, q1);
+    pp[0] = t1[0]; pp[1] = t1[1]; pp[2] = t1[2];
+    pp[3] = q1[0]; pp[4] = q1[1]; pp[5] = q1[2]; pp[6] = q1[3];
+  }
+}
+
+// ==========================================================================================
+// reprojection (cuda_ba.reproject, ba_cuda.cu:379-429; pops.transform, projective_ops.py:53-68)
+// ==========================================================================================
+template <bool CLAMP>
+__global__ void reproject_kernel(const float* __restrict__ poses, const float* __restrict__ patches,
+                                 const float* __restrict__ intrinsics, const int64_t* __restrict__ ii,
+                                 const int64_t* __restrict__ jj, const int64_t* __restrict__ kk,
+                                 float* __restrict__ coords, int64_t E, int P) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < E; n += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ix = ii[n], jx = jj[n], kx = kk[n];
+    const float* pi = poses + ix * 7;
+    const float* pj = poses + jx * 7;
+    float ti[3] = {pi[0], pi[1], pi[2]}, qi[4] = {pi[3], pi[4], pi[5], pi[6]};
+    float tj[3] = {pj[0], pj[1], pj[2]}, qj[4] = {pj[3], pj[4], pj[5], pj[6]};
+    const float* Ki = CLAMP ? intrinsics + ix * 4 : intrinsics;
+    const float* Kj = CLAMP ? intrinsics + jx * 4 : intrinsics;
+    if (CLAMP) {
+      // lietorch normalises quaternions when it loads a group element (so3.h:35-37)
+      const float ni = rsqrtf(qi[0] * qi[0] + qi[1] * qi[1] + qi[2] * qi[2] + qi[3] * qi[3]);
+      const float nj = rsqrtf(qj[0] * qj[0] + qj[1] * qj[1] + qj[2] * qj[2] + qj[3] * qj[3]);
+      for (int k = 0; k < 4; ++k) { qi[k] *= ni; qj[k] *= nj; }
+    }
+    float tij[3], qij[4];
+    relSE3(ti, qi, tj, qj, tij, qij);
+    const float* pk = patches + kx * 3 * P * P;
+    float* out = coords + n * 2 * P * P;
+    for (int i = 0; i < P * P; ++i) {
+      float Xi[4], Xj[3];
+      Xi[0] = (pk[i] - Ki[2]) / Ki[0];
+      Xi[1] = (pk[P * P + i] - Ki[3]) / Ki[1];
+      Xi[2] = 1.0f;
+      Xi[3] = pk[2 * P * P + i];
+      actSO3(qij, Xi, Xj);
+      Xj[0] += Xi[3] * tij[0]; Xj[1] += Xi[3] * tij[1]; Xj[2] += Xi[3] * tij[2];
+      if (CLAMP) {
+        const float d = 1.0f / fmaxf(Xj[2], 0.1f);
+        out[i] = Kj[0] * (d * Xj[0]) + Kj[2];
+        out[P * P + i] = Kj[1] * (d * Xj[1]) + Kj[3];
+      } else {
+        out[i] = Kj[0] * (Xj[0] / Xj[2]) + Kj[2];
+        out[P * P + i] = Kj[1] * (Xj[1] / Xj[2]) + Kj[3];
+      }
+    }
+  }
+}
+
+static inline int64_t al256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+}  // namespace dpvo
+
+using namespace dpvo;
+
+// ---- workspace layout ---------------------------------------------------------------------
+namespace {
+struct BaWs {
+  int32_t *k_order, *k_of, *k_start, *k_n; int64_t* k_key;
+  int32_t *p_order, *p_of, *p_start, *p_n; int64_t *p_key_i, *p_key_j;
+  float *Ed, *Qk, *uk, *rec, *dX;
+  void* gws_k; void* gws_p; int64_t gws_bytes;
+};
+int64_t ba_ws_layout(int64_t E, int N, char* base, BaWs* w) {
+  char* p = base;
+  auto take = [&](int64_t bytes) { char* r = p; p += al256(bytes); return r; };
+  const int64_t gb = dpvo_group_workspace_bytes(E);
+  char* k_order = take(E * 4); char* k_of = take(E * 4); char* k_start = take((E + 1) * 4);
+  char* k_key = take(E * 8); char* k_n = take(4);
+  char* p_order = take(E * 4); char* p_of = take(E * 4); char* p_start = take((E + 1) * 4);
+  char* p_ki = take(E * 8); char* p_kj = take(E * 8); char* p_n = take(4);
+  char* Ed = take(E * 6 * (int64_t)std::max(N, 1) * 4);
+  char* Qk = take(E * 4); char* uk = take(E * 4);
+  char* rec = take(E * (int64_t)BA_REC * 4);
+  char* dX = take(6 * BA_MAX_N * 4);
+  char* gk = take(gb); char* gp = take(gb);
+  if (w) {
+    w->k_order = (int32_t*)k_order; w->k_of = (int32_t*)k_of; w->k_start = (int32_t*)k_start;
+    w->k_key = (int64_t*)k_key; w->k_n = (int32_t*)k_n;
+    w->p_order = (int32_t*)p_order; w->p_of = (int32_t*)p_of; w->p_start = (int32_t*)p_start;
+    w->p_key_i = (int64_t*)p_ki; w->p_key_j = (int64_t*)p_kj; w->p_n = (int32_t*)p_n;
+    w->Ed = (float*)Ed; w->Qk = (float*)Qk; w->uk = (float*)uk; w->rec = (float*)rec; w->dX = (float*)dX;
+    w->gws_k = gk; w->gws_p = gp; w->gws_bytes = gb;
+  }
+  return (int64_t)(p - base);
+}
+}  // namespace
+
+extern "C" int64_t dpvo_ba_workspace_bytes(int64_t E, int n_free_poses) {
+  if (E < 0) E = 0;
+  return ba_ws_layout(E, n_free_poses, nullptr, nullptr) + 256;
+}
+
+extern "C" int dpvo_ba_forward(float* poses, float* patches, const float* intrinsics,
+                               const float* target, const float* weight, const float* lmbda,
+                               const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                               int64_t E, int64_t n_poses, int64_t n_patches, int P,
+                               int t0, int t1, int iterations,
+                               void* workspace, int64_t workspace_bytes, void* stream) {
+  DPVO_REQUIRE(E >= 0 && P > 0 && iterations >= 0 && t1 >= t0, "ba_forward: bad sizes");
+  if (E == 0 || iterations == 0) return DPVO_OK;
+  DPVO_REQUIRE(poses && patches && intrinsics && target && weight && lmbda && ii && jj && kk && workspace,
+               "ba_forward: null pointer");
+  (void)n_poses; (void)n_patches;
+  const int N = t1 - t0;
+  if (N > BA_MAX_N) {
+    set_error("ba_forward: %d free poses > %d supported by the on-chip solver (use the block-sparse path)", N, BA_MAX_N);
+    return DPVO_ERR_UNSUPPORTED;
+  }
+  if (workspace_bytes < dpvo_ba_workspace_bytes(E, N)) {
+    set_error("ba_forward: workspace %lld B < required %lld B", (long long)workspace_bytes,
+              (long long)dpvo_ba_workspace_bytes(E, N));
+    return DPVO_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  BaWs w;
+  ba_ws_layout(E, N, base, &w);
+
+  int rc = dpvo_group_edges(kk, nullptr, nullptr, E, w.k_order, w.k_of, w.k_start, w.k_key, nullptr, w.k_n,
+                            w.gws_k, w.gws_bytes, st);
+  if (rc) return rc;
+  if (N > 0) {
+    rc = dpvo_group_edges(ii, jj, nullptr, E, w.p_order, w.p_of, w.p_start, w.p_key_i, w.p_key_j, w.p_n,
+                          w.gws_p, w.gws_bytes, st);
+    if (rc) return rc;
+  }
+
+  BaArgs a;
+  a.poses = poses; a.patches = patches; a.intrinsics = intrinsics; a.target = target; a.weight = weight;
+  a.lmbda = lmbda; a.ii = ii; a.jj = jj; a.kk = kk; a.E = E; a.P = P; a.t0 = t0; a.N = N;
+  a.k_order = w.k_order; a.k_start = w.k_start; a.k_key = w.k_key; a.k_n = w.k_n;
+  a.p_order = w.p_order; a.p_start = w.p_start; a.p_key_i = w.p_key_i; a.p_key_j = w.p_key_j; a.p_n = w.p_n;
+  a.p_hdr = (const GroupHeaderBA*)w.gws_p;
+  a.Ed = w.Ed; a.Qk = w.Qk; a.uk = w.uk; a.rec = w.rec; a.dX = w.dX;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveSmem));
+    if (e != cudaSuccess) return check_cuda(e, "ba_forward: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  const int red_blocks = sm_count() * 4;
+  for (int it = 0; it < iterations; ++it) {
+    ba_reduce_kernel<<<red_blocks, BA_RED_WARPS * 32, 0, st>>>(a);
+    DPVO_LAUNCH_CHECK("ba_reduce_kernel");
+    ba_solve_kernel<<<BA_CLUSTER, BA_SOLVE_THREADS, sizeof(SolveSmem), st>>>(a);
+    DPVO_LAUNCH_CHECK("ba_solve_kernel");
+  }
+  return DPVO_OK;
+}
+
+extern "C" int dpvo_reproject(const float* poses, const float* patches, const float* intrinsics,
+                              const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                              float* coords, int64_t E, int P, int clamp_depth, void* stream) {
+  DPVO_REQUIRE(E >= 0 && P > 0, "reproject: bad sizes");
+  if (E == 0) return DPVO_OK;
+  DPVO_REQUIRE(poses && patches && intrinsics && ii && jj && kk && coords, "reproject: null pointer");
+  const int threads = 128;
+  const unsigned blocks = (unsigned)std::min<int64_t>((E + threads - 1) / threads, (int64_t)sm_count() * 16);
+  if (clamp_depth) reproject_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(poses, patches, intrinsics, ii, jj, kk, coords, E, P);
+  else reproject_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(poses, patches, intrinsics, ii, jj, kk, coords, E, P);
+  DPVO_LAUNCH_CHECK("reproject_kernel");
+  return DPVO_OK;
+}

@@ -1,0 +1,358 @@
+// Torch-extension shims over the C-ABI of include/dpvo_b200.h.
+//
+// One translation unit defines four Python modules; the build copies the resulting shared object
+// to cuda_corr*.so, cuda_ba*.so, lietorch_backends*.so and dpvo_b200_ext*.so:
+//   cuda_corr          same pybind surface as dpvo/altcorr/correlation.cpp:57-62
+//   cuda_ba            same as dpvo/fastba/ba.cpp:183-188
+//   lietorch_backends  same as dpvo/lietorch/src/lietorch.cpp:286-316
+//   dpvo_b200_ext      the fused entry points that have no counterpart in the reference
+// The shims only adapt torch::Tensor -> (pointer, sizes, strides, current CUDA stream), allocate
+// outputs and raise RuntimeError on a non-zero status.  There is no CPU path: a CPU tensor is an
+// error, not a fallback.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <vector>
+
+#include "../../include/dpvo_b200.h"
+
+namespace {
+
+using torch::Tensor;
+
+void check(int rc, const char* what) {
+  if (rc != DPVO_OK) {
+    TORCH_CHECK(false, what, " failed (status ", rc, "): ", dpvo_last_error());
+  }
+}
+
+int dt(const Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kHalf: return DPVO_F16;
+    case at::kBFloat16: return DPVO_BF16;
+    case at::kFloat: return DPVO_F32;
+    case at::kDouble: return DPVO_F64;
+    default: TORCH_CHECK(false, "dpvo_b200: unsupported dtype ", t.scalar_type());
+  }
+  return -1;
+}
+
+void need_cuda(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), "dpvo_b200: ", name, " must be a CUDA tensor (this build has no CPU path)");
+}
+
+void* stream() { return (void*)at::cuda::getCurrentCUDAStream().stream(); }
+
+Tensor i64c(const Tensor& t) { return t.to(at::kLong).contiguous(); }
+Tensor f32c(const Tensor& t) { return t.to(at::kFloat).contiguous(); }
+
+std::vector<int64_t> strides5(const Tensor& t) {
+  TORCH_CHECK(t.dim() == 5, "dpvo_b200: expected a 5-d tensor");
+  return {t.stride(0), t.stride(1), t.stride(2), t.stride(3), t.stride(4)};
+}
+
+Tensor byte_ws(int64_t bytes, const Tensor& like) {
+  return torch::empty({bytes}, like.options().dtype(at::kByte));
+}
+
+// ------------------------------------------------------------------------------ cuda_corr
+std::vector<Tensor> corr_forward(Tensor fmap1, Tensor fmap2, Tensor coords, Tensor ii, Tensor jj, int radius) {
+  need_cuda(fmap1, "fmap1"); need_cuda(fmap2, "fmap2"); need_cuda(coords, "coords");
+  c10::cuda::CUDAGuard guard(fmap1.device());
+  TORCH_CHECK(fmap1.scalar_type() == fmap2.scalar_type(), "corr: fmap1/fmap2 dtype mismatch");
+  TORCH_CHECK(fmap1.dim() == 5 && fmap2.dim() == 5 && coords.dim() == 5, "corr: expected 5-d inputs");
+  coords = f32c(coords); ii = i64c(ii); jj = i64c(jj);
+  const int B = coords.size(0), M = coords.size(1), P = coords.size(3);
+  const int C = fmap1.size(2), O = 2 * radius + 1;
+  TORCH_CHECK(coords.size(2) == 2 && coords.size(4) == P, "corr: coords must be [B,M,2,P,P]");
+  TORCH_CHECK(fmap1.size(3) == P && fmap1.size(4) == P && fmap2.size(2) == C, "corr: feature shapes do not match");
+  TORCH_CHECK(ii.numel() == M && jj.numel() == M, "corr: index length mismatch");
+  Tensor out = torch::empty({B, M, O, O, P, P}, fmap1.options());
+  auto s1 = strides5(fmap1), s2 = strides5(fmap2);
+  check(dpvo_corr_forward(fmap1.data_ptr(), s1.data(), fmap2.data_ptr(), s2.data(), coords.data_ptr<float>(),
+                          ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), out.data_ptr(), 1, dt(fmap1), B, M, C, P,
+                          (int)fmap1.size(1), (int)fmap2.size(1), (int)fmap2.size(3), (int)fmap2.size(4), radius, stream()),
+        "cuda_corr.forward");
+  return {out};
+}
+
+std::vector<Tensor> corr_backward(Tensor fmap1, Tensor fmap2, Tensor coords, Tensor ii, Tensor jj, Tensor grad, int radius) {
+  need_cuda(fmap1, "fmap1"); need_cuda(fmap2, "fmap2"); need_cuda(grad, "corr_grad");
+  c10::cuda::CUDAGuard guard(fmap1.device());
+  coords = f32c(coords); ii = i64c(ii); jj = i64c(jj);
+  grad = grad.contiguous();
+  const int B = coords.size(0), M = coords.size(1), P = coords.size(3), C = fmap1.size(2);
+  Tensor g1 = torch::zeros_like(fmap1);
+  Tensor g2 = torch::zeros_like(fmap2);
+  auto s1 = strides5(fmap1), s2 = strides5(fmap2), gs1 = strides5(g1), gs2 = strides5(g2);
+  check(dpvo_corr_backward(fmap1.data_ptr(), s1.data(), fmap2.data_ptr(), s2.data(), coords.data_ptr<float>(),
+                           ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), grad.data_ptr(), dt(grad),
+                           g1.data_ptr(), gs1.data(), g2.data_ptr(), gs2.data(), dt(fmap1), B, M, C, P, (int)fmap1.size(1),
+                           (int)fmap2.size(1), (int)fmap2.size(3), (int)fmap2.size(4), radius, stream()),
+        "cuda_corr.backward");
+  return {g1, g2};
+}
+
+std::vector<Tensor> patchify_forward(Tensor net, Tensor coords, int radius) {
+  need_cuda(net, "net"); need_cuda(coords, "coords");
+  c10::cuda::CUDAGuard guard(net.device());
+  TORCH_CHECK(net.dim() == 4 && coords.dim() == 3 && coords.size(2) == 2, "patchify: net [B,C,H,W], coords [B,M,2]");
+  coords = f32c(coords);
+  const int B = coords.size(0), M = coords.size(1), C = net.size(1), D = 2 * radius + 2;
+  Tensor patches = torch::empty({B, M, C, D, D}, net.options());
+  std::vector<int64_t> s = {net.stride(0), net.stride(1), net.stride(2), net.stride(3)};
+  check(dpvo_patchify_forward(net.data_ptr(), s.data(), coords.data_ptr<float>(), patches.data_ptr(), dt(net),
+                              B, M, C, (int)net.size(2), (int)net.size(3), radius, stream()),
+        "cuda_corr.patchify_forward");
+  return {patches};
+}
+
+std::vector<Tensor> patchify_backward(Tensor net, Tensor coords, Tensor gradient, int radius) {
+  need_cuda(net, "net"); need_cuda(gradient, "gradient");
+  c10::cuda::CUDAGuard guard(net.device());
+  coords = f32c(coords);
+  gradient = gradient.to(net.scalar_type()).contiguous();
+  const int B = coords.size(0), M = coords.size(1), C = net.size(1);
+  Tensor g = torch::zeros(net.sizes(), net.options());
+  check(dpvo_patchify_backward(gradient.data_ptr(), coords.data_ptr<float>(), g.data_ptr(), dt(net), B, M, C,
+                               (int)net.size(2), (int)net.size(3), radius, stream()),
+        "cuda_corr.patchify_backward");
+  return {g};
+}
+
+// -------------------------------------------------------------------------------- cuda_ba
+std::vector<Tensor> ba_forward(Tensor poses, Tensor patches, Tensor intrinsics, Tensor target, Tensor weight,
+                               Tensor lmbda, Tensor ii, Tensor jj, Tensor kk, int PPF, int t0, int t1,
+                               int iterations, bool eff_impl) {
+  need_cuda(poses, "poses"); need_cuda(patches, "patches");
+  c10::cuda::CUDAGuard guard(poses.device());
+  TORCH_CHECK(!eff_impl, "cuda_ba.forward: eff_impl=True (block-sparse global BA, loop closure) is not built in dpvo_b200");
+  (void)PPF;
+  TORCH_CHECK(poses.is_contiguous() && patches.is_contiguous(), "cuda_ba.forward updates poses/patches in place: they must be contiguous");
+  TORCH_CHECK(poses.scalar_type() == at::kFloat && patches.scalar_type() == at::kFloat, "cuda_ba.forward: poses/patches must be float32");
+  const int P = patches.size(-1);
+  intrinsics = f32c(intrinsics).view({-1, 4});
+  target = f32c(target).view({-1, 2});
+  weight = f32c(weight).view({-1, 2});
+  lmbda = f32c(lmbda).view({-1});
+  ii = i64c(ii); jj = i64c(jj); kk = i64c(kk);
+  const int64_t E = ii.numel();
+  TORCH_CHECK(jj.numel() == E && kk.numel() == E && target.size(0) == E && weight.size(0) == E, "cuda_ba.forward: edge arrays disagree in length");
+  const int64_t n_poses = poses.numel() / 7, n_patches = patches.numel() / (3 * P * P);
+  const int64_t wsb = dpvo_ba_workspace_bytes(E, t1 - t0);
+  Tensor ws = byte_ws(wsb, poses);
+  check(dpvo_ba_forward(poses.data_ptr<float>(), patches.data_ptr<float>(), intrinsics.data_ptr<float>(),
+                        target.data_ptr<float>(), weight.data_ptr<float>(), lmbda.data_ptr<float>(),
+                        ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), kk.data_ptr<int64_t>(), E, n_poses, n_patches, P,
+                        t0, t1, iterations, ws.data_ptr(), wsb, stream()),
+        "cuda_ba.forward");
+  return {};
+}
+
+std::vector<Tensor> ba_neighbors(Tensor ii, Tensor jj) {
+  need_cuda(ii, "ii"); need_cuda(jj, "jj");
+  c10::cuda::CUDAGuard guard(ii.device());
+  ii = i64c(ii); jj = i64c(jj);
+  const int64_t E = ii.numel();
+  TORCH_CHECK(jj.numel() == E, "cuda_ba.neighbors: length mismatch");
+  Tensor ix = torch::empty({E}, ii.options()), jx = torch::empty({E}, ii.options());
+  const int64_t wsb = dpvo_neighbors_workspace_bytes(E);
+  Tensor ws = byte_ws(wsb, ii);
+  check(dpvo_neighbors(ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), E, ix.data_ptr<int64_t>(), jx.data_ptr<int64_t>(),
+                       ws.data_ptr(), wsb, stream()),
+        "cuda_ba.neighbors");
+  return {ix, jx};
+}
+
+Tensor reproject_impl(Tensor poses, Tensor patches, Tensor intrinsics, Tensor ii, Tensor jj, Tensor kk, int clamp) {
+  need_cuda(poses, "poses"); need_cuda(patches, "patches");
+  c10::cuda::CUDAGuard guard(poses.device());
+  const int P = patches.size(-1);
+  poses = f32c(poses); patches = f32c(patches); intrinsics = f32c(intrinsics);
+  ii = i64c(ii); jj = i64c(jj); kk = i64c(kk);
+  const int64_t E = ii.numel();
+  Tensor coords = torch::empty({1, E, 2, P, P}, poses.options());
+  check(dpvo_reproject(poses.data_ptr<float>(), patches.data_ptr<float>(), intrinsics.data_ptr<float>(),
+                       ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), kk.data_ptr<int64_t>(), coords.data_ptr<float>(), E, P,
+                       clamp, stream()),
+        "cuda_ba.reproject");
+  return coords;
+}
+Tensor ba_reproject(Tensor poses, Tensor patches, Tensor intrinsics, Tensor ii, Tensor jj, Tensor kk) {
+  return reproject_impl(poses, patches, intrinsics, ii, jj, kk, 0);
+}
+
+std::vector<Tensor> ba_solve_system(Tensor, Tensor, Tensor, Tensor, Tensor, float, float, int) {
+  TORCH_CHECK(false, "cuda_ba.solve_system (CPU sparse pose-graph solve, loop closure only) is not built in dpvo_b200");
+  return {};
+}
+
+// ------------------------------------------------------------------------ lietorch_backends
+#define CHECK_CONTIGUOUS(x) TORCH_CHECK(x.is_contiguous(), #x " must be contiguous")
+
+int emb_dim(int g) { return g == DPVO_SO3 ? 4 : g == DPVO_RXSO3 ? 5 : g == DPVO_SE3 ? 7 : 8; }
+int tan_dim(int g) { return g == DPVO_SO3 ? 3 : g == DPVO_RXSO3 ? 4 : g == DPVO_SE3 ? 6 : 7; }
+
+typedef int (*un_fn)(int, int, const void*, void*, int64_t, void*);
+typedef int (*bin_fn)(int, int, const void*, const void*, void*, int64_t, void*);
+typedef int (*unb_fn)(int, int, const void*, const void*, void*, int64_t, void*);
+typedef int (*binb_fn)(int, int, const void*, const void*, const void*, void*, void*, int64_t, void*);
+
+Tensor lie_unary(un_fn f, int g, Tensor x, int out_dim, const char* name) {
+  CHECK_CONTIGUOUS(x); need_cuda(x, name);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = torch::empty({x.size(0), out_dim}, x.options());
+  check(f(g, dt(x), x.data_ptr(), y.data_ptr(), x.size(0), stream()), name);
+  return y;
+}
+Tensor lie_binary(bin_fn f, int g, Tensor x, Tensor y, int out_dim, const char* name) {
+  CHECK_CONTIGUOUS(x); CHECK_CONTIGUOUS(y); need_cuda(x, name);
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.scalar_type() == y.scalar_type() && x.size(0) == y.size(0), name, ": operand mismatch");
+  Tensor z = torch::empty({x.size(0), out_dim}, x.options());
+  check(f(g, dt(x), x.data_ptr(), y.data_ptr(), z.data_ptr(), x.size(0), stream()), name);
+  return z;
+}
+std::vector<Tensor> lie_unary_bwd(unb_fn f, int g, Tensor grad, Tensor x, const char* name) {
+  CHECK_CONTIGUOUS(x); CHECK_CONTIGUOUS(grad); need_cuda(x, name);
+  c10::cuda::CUDAGuard guard(x.device());
+  grad = grad.to(x.scalar_type());
+  Tensor dx = torch::empty(x.sizes(), x.options());
+  check(f(g, dt(x), grad.data_ptr(), x.data_ptr(), dx.data_ptr(), x.size(0), stream()), name);
+  return {dx};
+}
+std::vector<Tensor> lie_binary_bwd(binb_fn f, int g, Tensor grad, Tensor x, Tensor y, const char* name) {
+  CHECK_CONTIGUOUS(x); CHECK_CONTIGUOUS(y); CHECK_CONTIGUOUS(grad); need_cuda(x, name);
+  c10::cuda::CUDAGuard guard(x.device());
+  grad = grad.to(x.scalar_type());
+  Tensor dx = torch::empty(x.sizes(), x.options()), dy = torch::empty(y.sizes(), y.options());
+  check(f(g, dt(x), grad.data_ptr(), x.data_ptr(), y.data_ptr(), dx.data_ptr(), dy.data_ptr(), x.size(0), stream()), name);
+  return {dx, dy};
+}
+
+Tensor l_expm(int g, Tensor a) { return lie_unary(dpvo_lie_exp, g, a, emb_dim(g), "lietorch_backends.expm"); }
+std::vector<Tensor> l_expm_b(int g, Tensor grad, Tensor a) { return lie_unary_bwd(dpvo_lie_exp_backward, g, grad, a, "lietorch_backends.expm_backward"); }
+Tensor l_logm(int g, Tensor X) { return lie_unary(dpvo_lie_log, g, X, tan_dim(g), "lietorch_backends.logm"); }
+std::vector<Tensor> l_logm_b(int g, Tensor grad, Tensor X) { return lie_unary_bwd(dpvo_lie_log_backward, g, grad, X, "lietorch_backends.logm_backward"); }
+Tensor l_inv(int g, Tensor X) { return lie_unary(dpvo_lie_inv, g, X, emb_dim(g), "lietorch_backends.inv"); }
+std::vector<Tensor> l_inv_b(int g, Tensor grad, Tensor X) { return lie_unary_bwd(dpvo_lie_inv_backward, g, grad, X, "lietorch_backends.inv_backward"); }
+Tensor l_mul(int g, Tensor X, Tensor Y) { return lie_binary(dpvo_lie_mul, g, X, Y, emb_dim(g), "lietorch_backends.mul"); }
+std::vector<Tensor> l_mul_b(int g, Tensor grad, Tensor X, Tensor Y) { return lie_binary_bwd(dpvo_lie_mul_backward, g, grad, X, Y, "lietorch_backends.mul_backward"); }
+Tensor l_adj(int g, Tensor X, Tensor a) { return lie_binary(dpvo_lie_adj, g, X, a, tan_dim(g), "lietorch_backends.adj"); }
+std::vector<Tensor> l_adj_b(int g, Tensor grad, Tensor X, Tensor a) { return lie_binary_bwd(dpvo_lie_adj_backward, g, grad, X, a, "lietorch_backends.adj_backward"); }
+Tensor l_adjT(int g, Tensor X, Tensor a) { return lie_binary(dpvo_lie_adjT, g, X, a, tan_dim(g), "lietorch_backends.adjT"); }
+std::vector<Tensor> l_adjT_b(int g, Tensor grad, Tensor X, Tensor a) { return lie_binary_bwd(dpvo_lie_adjT_backward, g, grad, X, a, "lietorch_backends.adjT_backward"); }
+Tensor l_act(int g, Tensor X, Tensor p) { return lie_binary(dpvo_lie_act, g, X, p, 3, "lietorch_backends.act"); }
+std::vector<Tensor> l_act_b(int g, Tensor grad, Tensor X, Tensor p) { return lie_binary_bwd(dpvo_lie_act_backward, g, grad, X, p, "lietorch_backends.act_backward"); }
+Tensor l_act4(int g, Tensor X, Tensor p) { return lie_binary(dpvo_lie_act4, g, X, p, 4, "lietorch_backends.act4"); }
+std::vector<Tensor> l_act4_b(int g, Tensor grad, Tensor X, Tensor p) { return lie_binary_bwd(dpvo_lie_act4_backward, g, grad, X, p, "lietorch_backends.act4_backward"); }
+Tensor l_as_matrix(int g, Tensor X) {
+  CHECK_CONTIGUOUS(X); need_cuda(X, "X");
+  c10::cuda::CUDAGuard guard(X.device());
+  Tensor T = torch::empty({X.size(0), 4, 4}, X.options());
+  check(dpvo_lie_as_matrix(g, dt(X), X.data_ptr(), T.data_ptr(), X.size(0), stream()), "lietorch_backends.as_matrix");
+  return T;
+}
+Tensor l_projector(int g, Tensor X) {
+  CHECK_CONTIGUOUS(X); need_cuda(X, "X");
+  c10::cuda::CUDAGuard guard(X.device());
+  const int n = emb_dim(g);
+  Tensor Pm = torch::empty({X.size(0), n, n}, X.options());
+  check(dpvo_lie_projector(g, dt(X), X.data_ptr(), Pm.data_ptr(), X.size(0), stream()), "lietorch_backends.projector");
+  return Pm;
+}
+Tensor l_jinv(int g, Tensor X, Tensor a) { return lie_binary(dpvo_lie_jinv, g, X, a, tan_dim(g), "lietorch_backends.Jinv"); }
+
+// ------------------------------------------------------------------------- dpvo_b200_ext
+// DPVO.corr (dpvo.py:200-207) in one launch: returns [1, E, 882]-compatible [B,M,O,O,P,P,2]
+Tensor corr_pyramid2(Tensor fmap1, Tensor fmap2_l0, Tensor fmap2_l1, Tensor coords, Tensor ii, Tensor jj, int radius, double div) {
+  need_cuda(fmap1, "fmap1");
+  c10::cuda::CUDAGuard guard(fmap1.device());
+  coords = f32c(coords); ii = i64c(ii); jj = i64c(jj);
+  const int B = coords.size(0), M = coords.size(1), P = coords.size(3), C = fmap1.size(2), O = 2 * radius + 1;
+  Tensor out = torch::empty({B, M, O, O, P, P, 2}, fmap1.options());
+  auto s1 = strides5(fmap1), s20 = strides5(fmap2_l0), s21 = strides5(fmap2_l1);
+  check(dpvo_corr_forward_pyramid2(fmap1.data_ptr(), s1.data(), fmap2_l0.data_ptr(), s20.data(), (int)fmap2_l0.size(3),
+                                   (int)fmap2_l0.size(4), fmap2_l1.data_ptr(), s21.data(), (int)fmap2_l1.size(3),
+                                   (int)fmap2_l1.size(4), (float)div, coords.data_ptr<float>(), ii.data_ptr<int64_t>(),
+                                   jj.data_ptr<int64_t>(), out.data_ptr(), dt(fmap1), B, M, C, P, (int)fmap1.size(1),
+                                   (int)fmap2_l0.size(1), radius, stream()),
+        "dpvo_b200_ext.corr_pyramid2");
+  return out;
+}
+
+// returns (order, group_of, group_start, key_a, key_b, n_groups) -- all device tensors
+std::vector<Tensor> group_edges(Tensor key_a, c10::optional<Tensor> key_b, c10::optional<Tensor> sec) {
+  need_cuda(key_a, "key_a");
+  c10::cuda::CUDAGuard guard(key_a.device());
+  key_a = i64c(key_a);
+  const int64_t E = key_a.numel();
+  Tensor kb, sc;
+  if (key_b.has_value()) kb = i64c(*key_b);
+  if (sec.has_value()) sc = i64c(*sec);
+  auto oi = key_a.options().dtype(at::kInt);
+  Tensor order = torch::empty({E}, oi), gof = torch::empty({E}, oi), gstart = torch::empty({E + 1}, oi);
+  Tensor ka = torch::empty({E}, key_a.options()), kbo = torch::empty({E}, key_a.options()), ng = torch::empty({1}, oi);
+  const int64_t wsb = dpvo_group_workspace_bytes(E);
+  Tensor ws = byte_ws(wsb, key_a);
+  check(dpvo_group_edges(key_a.data_ptr<int64_t>(), kb.defined() ? kb.data_ptr<int64_t>() : nullptr,
+                         sc.defined() ? sc.data_ptr<int64_t>() : nullptr, E, order.data_ptr<int>(), gof.data_ptr<int>(),
+                         gstart.data_ptr<int>(), ka.data_ptr<int64_t>(), kbo.data_ptr<int64_t>(), ng.data_ptr<int>(),
+                         ws.data_ptr(), wsb, stream()),
+        "dpvo_b200_ext.group_edges");
+  return {order, gof, gstart, ka, kbo, ng};
+}
+
+Tensor reproject_clamped(Tensor poses, Tensor patches, Tensor intrinsics, Tensor ii, Tensor jj, Tensor kk) {
+  return reproject_impl(poses, patches, intrinsics, ii, jj, kk, 1);
+}
+
+int64_t launch_count() { return dpvo_launch_count(); }
+std::string version() { return dpvo_version(); }
+
+}  // namespace
+
+PYBIND11_MODULE(cuda_corr, m) {
+  m.def("forward", &corr_forward, "CORR forward");
+  m.def("backward", &corr_backward, "CORR backward");
+  m.def("patchify_forward", &patchify_forward, "PATCHIFY forward");
+  m.def("patchify_backward", &patchify_backward, "PATCHIFY backward");
+}
+
+PYBIND11_MODULE(cuda_ba, m) {
+  m.def("forward", &ba_forward, "BA forward operator");
+  m.def("neighbors", &ba_neighbors, "temporal neighbor indices");
+  m.def("reproject", &ba_reproject, "fused reprojection");
+  m.def("solve_system", &ba_solve_system, "pose-graph solve (not built)");
+}
+
+PYBIND11_MODULE(lietorch_backends, m) {
+  m.def("expm", &l_expm, "exp map forward");
+  m.def("expm_backward", &l_expm_b, "exp map backward");
+  m.def("logm", &l_logm, "log map forward");
+  m.def("logm_backward", &l_logm_b, "log map backward");
+  m.def("inv", &l_inv, "inverse operator");
+  m.def("inv_backward", &l_inv_b, "inverse operator backward");
+  m.def("mul", &l_mul, "group operator");
+  m.def("mul_backward", &l_mul_b, "group operator backward");
+  m.def("adj", &l_adj, "adjoint operator");
+  m.def("adj_backward", &l_adj_b, "adjoint operator backward");
+  m.def("adjT", &l_adjT, "transposed adjoint operator");
+  m.def("adjT_backward", &l_adjT_b, "transposed adjoint operator backward");
+  m.def("act", &l_act, "action on point");
+  m.def("act_backward", &l_act_b, "action on point backward");
+  m.def("act4", &l_act4, "action on homogeneous point");
+  m.def("act4_backward", &l_act4_b, "action on homogeneous point backward");
+  m.def("as_matrix", &l_as_matrix, "convert to matrix");
+  m.def("projector", &l_projector, "orthogonal projection matrix");
+  m.def("Jinv", &l_jinv, "left inverse jacobian operator");
+}
+
+PYBIND11_MODULE(dpvo_b200_ext, m) {
+  m.def("corr_pyramid2", &corr_pyramid2, "two-level fused correlation");
+  m.def("group_edges", &group_edges, "device edge grouping", py::arg("key_a"), py::arg("key_b") = py::none(),
+        py::arg("sec") = py::none());
+  m.def("reproject_clamped", &reproject_clamped, "pops.transform-compatible fused reprojection");
+  m.def("launch_count", &launch_count, "kernel launches issued by libdpvo_b200 so far");
+  m.def("version", &version, "library version string");
+}

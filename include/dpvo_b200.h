@@ -1,0 +1,309 @@
+/*
+ * dpvo_b200.h -- C-ABI of the B200-native DPVO update hot path.
+ *
+ * Every entry point takes plain device pointers, sizes/strides and a CUDA stream and
+ * returns an int status (DPVO_OK == 0).  No torch types cross this boundary.  The three
+ * torch-extension shims (cuda_corr / cuda_ba / lietorch_backends, see dpvo_b200/csrc/shim.cpp)
+ * adapt torch::Tensor -> these calls and keep the reference's pybind names and signatures.
+ *
+ * Reference interfaces replaced (paths relative to the princeton-vl/DPVO tree):
+ *   cuda_corr          dpvo/altcorr/correlation.cpp:57-62, correlation_kernel.cu:193-333
+ *   cuda_ba            dpvo/fastba/ba.cpp:183-188, ba_cuda.cu:433-617
+ *   lietorch_backends  dpvo/lietorch/src/lietorch.cpp:286-316, lietorch_gpu.cu:298-601
+ *   Update operator    dpvo/net.py:27-92, dpvo/blocks.py:15-48 (pieces: LayerNorm, SoftAgg, GEMMs)
+ *
+ * All pointers are DEVICE pointers unless stated otherwise.  `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  Kernels are compiled for sm_100a only;
+ * there is no CPU fallback: a call on a machine without a usable device returns DPVO_ERR_CUDA.
+ */
+#ifndef DPVO_B200_H
+#define DPVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------- */
+#define DPVO_OK               0
+#define DPVO_ERR_INVALID      1   /* bad argument (null pointer, negative size, bad dtype) */
+#define DPVO_ERR_UNSUPPORTED  2   /* valid request outside what this build implements      */
+#define DPVO_ERR_CUDA         3   /* CUDA runtime error; see dpvo_last_error()             */
+#define DPVO_ERR_WORKSPACE    4   /* workspace too small                                   */
+
+/* ---- element types (match at::ScalarType semantics, not values) --------------------- */
+#define DPVO_F16  0
+#define DPVO_F32  1
+#define DPVO_F64  2
+#define DPVO_BF16 3
+
+/* ---- Lie group ids: lietorch/include/dispatch.h:12-32 -------------------------------- */
+#define DPVO_SO3   1
+#define DPVO_RXSO3 2
+#define DPVO_SE3   3
+#define DPVO_SIM3  4
+
+const char* dpvo_version(void);
+/* Thread-local text of the last non-OK status produced by this library. */
+const char* dpvo_last_error(void);
+/* Number of kernel launches issued by this library since process start (all entry points). */
+int64_t dpvo_launch_count(void);
+
+/* ======================================================================================
+ * cuda_corr  (altcorr)
+ * ====================================================================================== */
+
+/*
+ * cuda_corr.forward -- correlation_kernel.cu:193-233 (kernel :82-136 + bilinear blend :221-230
+ * + permute :232), fused into one launch.
+ *
+ *   fmap1   logical [B, S1, C, P, P]   patch features, indexed by ii[m]   (gmap)
+ *   fmap2   logical [B, S2, C, H2, W2] frame features, indexed by jj[m]   (pyramid level)
+ *   coords  contiguous fp32 [B, M, 2, P, P]   (x, y) per patch pixel
+ *   ii, jj  int64 [M]
+ *   out     logical [B, M, 2R+1 (x offset), 2R+1 (y offset), P, P], element (b,m,xo,yo,i,j)
+ *           stored at out[((((b*M+m)*(2R+1)+xo)*(2R+1)+yo)*P+i)*P+j) * out_elem_stride].
+ *           out_elem_stride = 1 gives the reference's (contiguous) result; 2 lets two pyramid
+ *           levels interleave into the [B, M, 882] layout DPVO.corr builds with torch.stack
+ *           (dpvo/dpvo.py:207).
+ *   fmapX_strides: element strides of the 5 logical dims (any layout; channels-last, i.e.
+ *           stride[2] == 1, is the fast path for fp16).
+ *   dtype   element type of fmap1, fmap2 and out (F16 / F32 / F64 / BF16).
+ * Out-of-image taps contribute exactly 0 (correlation_kernel.cu:121-122).  Accumulation is
+ * fp32 (fp64 for F64) -- the reference accumulates in the input type (:121).
+ */
+int dpvo_corr_forward(const void* fmap1, const int64_t* fmap1_strides,
+                      const void* fmap2, const int64_t* fmap2_strides,
+                      const float* coords, const int64_t* ii, const int64_t* jj,
+                      void* out, int64_t out_elem_stride,
+                      int dtype, int B, int M, int C, int P,
+                      int S1, int S2, int H2, int W2, int radius, void* stream);
+
+/*
+ * Two-level fused form of DPVO.corr (dpvo/dpvo.py:200-207): level 0 samples fmap2_l0 at coords,
+ * level 1 samples fmap2_l1 at coords / lvl1_div (4 in DPVO), result written as
+ * out[B, M, 2R+1, 2R+1, P, P, 2] (level innermost) == torch.stack([c0, c1], -1).
+ * B must be 1 batch stride aware through strides as above.
+ */
+int dpvo_corr_forward_pyramid2(const void* fmap1, const int64_t* fmap1_strides,
+                               const void* fmap2_l0, const int64_t* l0_strides, int H0, int W0,
+                               const void* fmap2_l1, const int64_t* l1_strides, int H1, int W1,
+                               float lvl1_div,
+                               const float* coords, const int64_t* ii, const int64_t* jj,
+                               void* out,
+                               int dtype, int B, int M, int C, int P,
+                               int S1, int S2, int radius, void* stream);
+
+/*
+ * cuda_corr.backward -- correlation_kernel.cu:236-286 (bilinear-transpose :252-269 + kernel
+ * :139-190) fused.  grad is logical [B, M, 2R+1(x), 2R+1(y), P, P], contiguous, element type
+ * grad_dtype (fp32, or the feature dtype).  fmap1_grad / fmap2_grad are shaped like fmap1 /
+ * fmap2 with the given element strides (torch::zeros_like keeps the input layout) and MUST be
+ * zero-filled by the caller; gradients are accumulated with atomics as in the reference, but
+ * one atomic per touched (pixel, channel) instead of one per tap.  No gradient w.r.t. coords.
+ */
+int dpvo_corr_backward(const void* fmap1, const int64_t* fmap1_strides,
+                       const void* fmap2, const int64_t* fmap2_strides,
+                       const float* coords, const int64_t* ii, const int64_t* jj,
+                       const void* grad, int grad_dtype,
+                       void* fmap1_grad, const int64_t* fmap1_grad_strides,
+                       void* fmap2_grad, const int64_t* fmap2_grad_strides,
+                       int dtype, int B, int M, int C, int P,
+                       int S1, int S2, int H2, int W2, int radius, void* stream);
+
+/*
+ * cuda_corr.patchify_forward -- correlation_kernel.cu:288-307 (kernel :16-47).
+ *   net [B, C, H, W] (strided), coords fp32 [B, M, 2] contiguous,
+ *   patches [B, M, C, D, D] contiguous with D = 2R+2, zero where the window leaves the map.
+ * The whole output is written (no pre-zeroing needed).
+ */
+int dpvo_patchify_forward(const void* net, const int64_t* net_strides, const float* coords,
+                          void* patches, int dtype, int B, int M, int C, int H, int W,
+                          int radius, void* stream);
+
+/*
+ * cuda_corr.patchify_backward -- correlation_kernel.cu:310-333 (kernel :49-80).
+ *   gradient [B, M, C, D, D] contiguous; net_grad [B, C, H, W] contiguous, zero-filled by caller.
+ */
+int dpvo_patchify_backward(const void* gradient, const float* coords, void* net_grad,
+                           int dtype, int B, int M, int C, int H, int W, int radius,
+                           void* stream);
+
+/* ======================================================================================
+ * patch-graph index structure (replaces torch::_unique + CPU stable_sort in ba.cpp:59-97,
+ * torch.unique in blocks.py:41 and torch::_unique in ba_cuda.cu:447)
+ * ====================================================================================== */
+
+/*
+ * Group E edges by the pair key (key_a[e], key_b[e]) (key_b may be NULL -> key_a alone); the
+ * members of a group are ordered by (sec[e], e) (sec may be NULL -> ordered by e).  For
+ * |key_b| < mul this is the same partition as the scalar key key_a*mul + key_b that
+ * Update.forward builds (net.py:88: ii*12345 + jj).
+ * Outputs (all device):
+ *   order[E]          int32 edge ids sorted by (key_a, key_b, sec, e)
+ *   group_of[E]       int32 dense group id of every edge; groups numbered by ascending key
+ *   group_start[E+1]  int32 CSR offsets into order (entries [0..G] are written)
+ *   group_key_a[E], group_key_b[E]  int64 keys of every group ([0..G-1] written; key_b may be NULL)
+ *   n_groups[1]       int32 G
+ * workspace: dpvo_group_workspace_bytes(E) bytes.  Deterministic: stable radix sort, integer
+ * atomics only.
+ */
+int64_t dpvo_group_workspace_bytes(int64_t E);
+int dpvo_group_edges(const int64_t* key_a, const int64_t* key_b, const int64_t* sec, int64_t E,
+                     int32_t* order, int32_t* group_of, int32_t* group_start,
+                     int64_t* group_key_a, int64_t* group_key_b, int32_t* n_groups,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * cuda_ba.neighbors -- ba.cpp:59-97.  For every edge e: ix[e] = the edge preceding e and
+ * jx[e] = the edge following e among the edges with the same ii value, ordered by
+ * (jj, original position) (std::stable_sort semantics); -1 at the ends.  int64 outputs.
+ * workspace: dpvo_neighbors_workspace_bytes(E).
+ */
+int64_t dpvo_neighbors_workspace_bytes(int64_t E);
+int dpvo_neighbors(const int64_t* ii, const int64_t* jj, int64_t E,
+                   int64_t* ix, int64_t* jx,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ======================================================================================
+ * cuda_ba  (fastba)
+ * ====================================================================================== */
+
+/*
+ * cuda_ba.forward, eff_impl == false -- ba_cuda.cu:433-582.  `iterations` Gauss-Newton steps
+ * over poses [t0, t1) and the inverse depth of every patch referenced by kk, IN PLACE.
+ *   poses      fp32 [n_poses, 7]  (tx ty tz qx qy qz qw)
+ *   patches    fp32 [n_patches, 3, P, P]
+ *   intrinsics fp32 [>=1, 4]  (row 0 is used for every edge: ba_cuda.cu:253-259)
+ *   target, weight fp32 [E, 2];  lmbda fp32 [1];  ii, jj, kk int64 [E]
+ * Damping S += I*(1e-4*S + 1) (:560), Q = 1/(C + lmbda) (:519), retractions :157-229.
+ * Requires t1 - t0 <= 32 (dense 6N x 6N system held on chip); t1 - t0 == 0 is the
+ * structure-only branch (:521-531).  workspace: dpvo_ba_workspace_bytes(E, t1 - t0).
+ */
+int64_t dpvo_ba_workspace_bytes(int64_t E, int n_free_poses);
+int dpvo_ba_forward(float* poses, float* patches, const float* intrinsics,
+                    const float* target, const float* weight, const float* lmbda,
+                    const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                    int64_t E, int64_t n_poses, int64_t n_patches, int P,
+                    int t0, int t1, int iterations,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * cuda_ba.reproject -- ba_cuda.cu:585-617 (kernel :379-429): coords fp32 [E, 2, P, P].
+ * clamp_depth = 0 reproduces the kernel (divide by raw Z, :422-423, intrinsics row 0);
+ * clamp_depth = 1 reproduces pops.transform (projective_ops.py:53-68: Z clamped to >= 0.1 in
+ * proj :43, per-edge intrinsics rows ii / jj), the form DPVO.reproject feeds to corr.
+ */
+int dpvo_reproject(const float* poses, const float* patches, const float* intrinsics,
+                   const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                   float* coords, int64_t E, int P, int clamp_depth, void* stream);
+
+/* ======================================================================================
+ * lietorch_backends
+ * ====================================================================================== */
+/*
+ * One entry per pybind function of lietorch.cpp:286-316.  group = DPVO_SO3..DPVO_SIM3,
+ * dtype = DPVO_F32 / DPVO_F64, n = batch (number of group elements), all tensors contiguous
+ * [n, dim].  Embedding widths: SO3 4, RxSO3 5, SE3 7, Sim3 8; tangent widths 3, 4, 6, 7.
+ * Backward functions follow lietorch_gpu.cu:32-256 (left-tangent gradients; gradients w.r.t.
+ * group elements have the embedding width with the last component 0).
+ */
+int dpvo_lie_exp(int group, int dtype, const void* a, void* X, int64_t n, void* stream);
+int dpvo_lie_exp_backward(int group, int dtype, const void* grad, const void* a, void* da,
+                          int64_t n, void* stream);
+int dpvo_lie_log(int group, int dtype, const void* X, void* a, int64_t n, void* stream);
+int dpvo_lie_log_backward(int group, int dtype, const void* grad, const void* X, void* dX,
+                          int64_t n, void* stream);
+int dpvo_lie_inv(int group, int dtype, const void* X, void* Y, int64_t n, void* stream);
+int dpvo_lie_inv_backward(int group, int dtype, const void* grad, const void* X, void* dX,
+                          int64_t n, void* stream);
+int dpvo_lie_mul(int group, int dtype, const void* X, const void* Y, void* Z, int64_t n,
+                 void* stream);
+int dpvo_lie_mul_backward(int group, int dtype, const void* grad, const void* X, const void* Y,
+                          void* dX, void* dY, int64_t n, void* stream);
+int dpvo_lie_adj(int group, int dtype, const void* X, const void* a, void* b, int64_t n,
+                 void* stream);
+int dpvo_lie_adj_backward(int group, int dtype, const void* grad, const void* X, const void* a,
+                          void* dX, void* da, int64_t n, void* stream);
+int dpvo_lie_adjT(int group, int dtype, const void* X, const void* a, void* b, int64_t n,
+                  void* stream);
+int dpvo_lie_adjT_backward(int group, int dtype, const void* grad, const void* X, const void* a,
+                           void* dX, void* da, int64_t n, void* stream);
+int dpvo_lie_act(int group, int dtype, const void* X, const void* p, void* q, int64_t n,
+                 void* stream);
+int dpvo_lie_act_backward(int group, int dtype, const void* grad, const void* X, const void* p,
+                          void* dX, void* dp, int64_t n, void* stream);
+int dpvo_lie_act4(int group, int dtype, const void* X, const void* p, void* q, int64_t n,
+                  void* stream);
+int dpvo_lie_act4_backward(int group, int dtype, const void* grad, const void* X, const void* p,
+                           void* dX, void* dp, int64_t n, void* stream);
+int dpvo_lie_as_matrix(int group, int dtype, const void* X, void* T, int64_t n, void* stream);
+int dpvo_lie_projector(int group, int dtype, const void* X, void* Pm, int64_t n, void* stream);
+int dpvo_lie_jinv(int group, int dtype, const void* X, const void* a, void* b, int64_t n,
+                  void* stream);
+
+/* ======================================================================================
+ * Update operator building blocks (dpvo/net.py:27-92, dpvo/blocks.py:15-48)
+ * ====================================================================================== */
+
+/*
+ * y[r, :] = LayerNorm(a[r] + b[r] + c[r]) * gamma + beta   (b, c optional, may be NULL)
+ * rows x dim, eps as given (1e-3 in Update: net.py:41,47,49,57).  a/b/c dtype in_dtype
+ * (per-tensor: in_dtypes[3]), y dtype out_dtype; gamma/beta fp32.  Statistics in fp32.
+ */
+int dpvo_add_layernorm(const void* a, const void* b, const void* c, const int* in_dtypes,
+                       const float* gamma, const float* beta, float eps,
+                       void* y, int out_dtype, int64_t rows, int dim, void* stream);
+
+/*
+ * Neighbour gather with mask (net.py:81-85): y[e, :] = (idx[e] >= 0) ? x[idx[e], :] : 0.
+ */
+int dpvo_gather_rows_masked(const void* x, int x_dtype, const int64_t* idx,
+                            void* y, int y_dtype, int64_t rows, int dim, void* stream);
+
+/*
+ * SoftAgg reduction (blocks.py:40-43, torch_scatter 2.1.2 scatter_softmax + scatter_sum):
+ *   y[g, c] = sum_{e in group g} f[e, c] * exp(gl[e, c] - max_g) / sum_{e in g} exp(gl[e,c]-max_g)
+ * using the CSR from dpvo_group_edges (order, group_start, G groups).  f, gl: [E, dim]
+ * dtype in_dtype; y: [G, dim] dtype out_dtype.  G is read from n_groups (device) and y rows
+ * beyond G are untouched; max_groups bounds the launch.
+ */
+int dpvo_softagg_reduce(const void* f, const void* gl, int in_dtype,
+                        const int32_t* order, const int32_t* group_start,
+                        const int32_t* n_groups, int64_t max_groups,
+                        void* y, int out_dtype, int dim, void* stream);
+
+/*
+ * net[e, :] += h[group_of[e], :]   (the `[:, jx]` expand of blocks.py:46 fused with the
+ * residual add of net.py:87-88).  net fp32 or fp16 in place.
+ */
+int dpvo_scatter_add_rows(void* net, int net_dtype, const void* h, int h_dtype,
+                          const int32_t* group_of, int64_t rows, int dim, void* stream);
+
+/*
+ * Dense layer on tensor cores (tcgen05, fp16 operands, fp32 accumulate in TMEM):
+ *   Y = epilogue( X[rows, K] @ W[N, K]^T + bias[N] )
+ * X, W fp16 row-major (K contiguous), bias fp32.  Epilogue selected by `epilogue`:
+ *   DPVO_EPI_NONE      y = acc + bias
+ *   DPVO_EPI_RELU      y = relu(acc + bias)
+ *   DPVO_EPI_SIGMOID   y = sigmoid(acc + bias)
+ *   DPVO_EPI_RESADD    y = res + acc + bias                      (res: [rows, N] res_dtype)
+ *   DPVO_EPI_GATEDRES  y = res + gate * (acc + bias)             (gate: [rows, N] fp16)
+ * Y dtype y_dtype (F16 or F32).  K % 16 == 0 after caller padding (882 -> 896), N % 16 == 0,
+ * N <= 384.  Row tails are handled.
+ */
+#define DPVO_EPI_NONE     0
+#define DPVO_EPI_RELU     1
+#define DPVO_EPI_SIGMOID  2
+#define DPVO_EPI_RESADD   3
+#define DPVO_EPI_GATEDRES 4
+int dpvo_linear_f16(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                    const void* res, int res_dtype, const void* gate,
+                    void* Y, int y_dtype, int64_t ldy,
+                    int64_t rows, int N, int K, int epilogue, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPVO_B200_H */
