@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- update-iteration throughput of the DPVO hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config default|fast]
+
+One "step" = one DPVO.update() (dpvo/dpvo.py:328-360): reprojection, 2-level patch correlation,
+update operator, 2 Gauss-Newton BA iterations, on the steady-state synthetic patch graph of
+BASELINE.json configs[1] (480x640, 96 patches/frame, 10-pose window, E = 47,712 edges; one update per
+frame in steady state, so steps/s == frames/s of the hot path).  N > 1 runs one independent stream per
+GPU (no collective on the data path): whole-job value = N * stream rate, scaling "weak".
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same step through the
+public API with the new frame coming from pinned host memory and poses/depths read back to the host.
+`roofline` is for the dominant kernel (correlation): algorithmic bytes (50,492 B/edge at
+fp16) / measured kernel time vs the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`--impl reference` times the reference's CPU path (oracle port of F.grid_sample correlation + PyTorch
+Update + dpvo/ba.py BA, BASELINE.json configs[0] style) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_EDGE_FP16 = 50492      # SURVEY 8(d), both pyramid levels, s = 2 bytes
+METRIC = "VO frames/sec of the update hot path (corr + update operator + BA per frame)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU path
+def cpu_reference_step_factory(config, sample_stride, threads):
+    """The reference's CPU implementation of one update() on the edges of every `sample_stride`-th
+    patch of the SAME synthetic graph: grid_sample correlation (2 levels) + Update (fp32 torch) +
+    2 x dpvo/ba.py BA.  Returns (step_fn, E_sample, E_full)."""
+    import torch
+    from dpvo_b200 import synthetic
+    from oracle import ba as OB, corr as OC, update as OU
+    torch.set_num_threads(threads)
+    st = synthetic.make_state(config, 36 if config == "default" else 30, device="cpu", features=False)
+    M = st.cfg["M"]
+    keep = (st.kk % sample_stride) == 0
+    ii, jj, kk = st.ii[keep], st.jj[keep], st.kk[keep]
+    E = int(keep.sum())
+    g = torch.Generator().manual_seed(5)
+    frames = sorted(set(jj.tolist()))
+    h, w = st.cfg["ht"] // 4, st.cfg["wd"] // 4
+    remap = {f: i for i, f in enumerate(frames)}
+    jl = torch.tensor([remap[int(j)] for j in jj])
+    fmap1 = torch.randn(1, len(frames), 128, h, w, generator=g) / 4
+    fmap2 = torch.nn.functional.avg_pool2d(fmap1[0], 4, 4)[None]
+    pk = torch.unique(kk)
+    kl = torch.searchsorted(pk, kk)
+    gmap = torch.randn(1, len(pk), 128, 3, 3, generator=g) / 4
+    imap = torch.randn(1, len(pk), 384, generator=g) / 4
+    torch.manual_seed(1234)
+    upd = OU.Update(3).eval()
+    net = torch.zeros(1, E, 384)
+    poses, patches, intr = st.poses[None], st.patches[None], st.intrinsics[None]
+    bounds = [-64, -64, w + 64, h + 64]
+
+    def step():
+        with torch.no_grad():
+            coords = OB.transform(poses, patches, intr, ii, jj, kk).permute(0, 1, 4, 2, 3).contiguous()
+            c0 = OC.corr_grid_sample(gmap, fmap1, coords, kl, jl, 3)
+            c1 = OC.corr_grid_sample(gmap, fmap2, coords / 4, kl, jl, 3)
+            corr = torch.stack([c0, c1], -1).view(1, E, -1)
+            n2, (delta, weight, _) = upd(net, imap[:, kl], corr, None, ii, jj, kk)
+            target = coords[..., 1, 1] + delta
+            P, Q = poses, patches
+            for _ in range(2):
+                P, Q = OB.python_ba(P, Q, intr, target, weight, 1e-4, ii, jj, kk, bounds, ep=10.0, fixedp=1)
+        return P
+
+    return step, E, st.E
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    stride = 24 if args.config == "default" else 8
+    step, Es, Ef = cpu_reference_step_factory(args.config, stride, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    full = dt * Ef / Es                      # seconds per full update, linear in the edge count
+    val = args.gpus * 1.0 / full if False else 1.0 / full
+    sample = "edges of every %dth patch: %d of %d edges per step, time scaled by %d/%d" % (stride, Es, Ef, Ef, Es)
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args.config, Ef),
+           "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def workload_config(config, E):
+    if config == "default":
+        w = "BASELINE configs[1]: synthetic 480x640 stream, default.yaml (96 patches, 10-pose window), E=%d edges, 2208 live patches" % E
+    else:
+        w = "BASELINE configs[2]: synthetic 480x752 stream, fast.yaml (48 patches, 7-pose window), E=%d edges" % E
+    return {"workload": w, "edges": E, "l2_policy": "inputs larger than L2 (fp16 feature ring 188 MB > 126 MB L2); no flush",
+            "parallelism": "one independent stream per GPU, no collectives"}
+
+
+# ------------------------------------------------------------------------------------ GPU path
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    import dpvo_b200
+    from dpvo_b200 import synthetic
+    from dpvo_b200.runner import UpdateRunner
+    ex = dpvo_b200.extensions()[3]
+
+    n_frames = 36 if args.config == "default" else 30
+    st = synthetic.make_state(args.config, n_frames, device=dev, seed=1234 + rank)
+    run = UpdateRunner(st, gemm=args.gemm)
+    E = st.E
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident loop
+    for _ in range(max(args.warmup, 3)):
+        run.reset(); run.step()
+    sampler = ClockSampler(local)
+    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] for k in ("corr0", "corr1", "ba0", "ba1")}
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ex.launch_count()
+    t_start.record()
+    for i in range(args.steps):
+        run.timers = {k: v[i] for k, v in ev.items()}
+        run.reset()
+        run.step()
+    t_end.record()
+    barrier()
+    launches = ex.launch_count() - l0
+    run.timers = None
+    ms = t_start.elapsed_time(t_end) / args.steps
+    corr_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(ev["corr0"], ev["corr1"]))
+    ba_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(ev["ba0"], ev["ba1"]))
+
+    # ---- end to end: new frame from pinned host memory every step, poses + depths back to host
+    hf = run.make_host_frame()
+    out_p = torch.empty(st.n, 7, pin_memory=True)
+    out_d = torch.empty(st.n * run.M, pin_memory=True)
+    for _ in range(3):
+        run.reset(); run.step_e2e(hf, out_p, out_d)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run.reset()
+        h2d, d2h = run.step_e2e(hf, out_p, out_d)
+        torch.cuda.current_stream().synchronize()          # the host consumes the result of every frame
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms, corr_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, corr_ms = [float(x) for x in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, which = peaks()
+    ach = BYTES_PER_EDGE_FP16 * E / (corr_ms * 1e-3) / 1e9
+    out = {"metric": METRIC, "value": world * 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f16 operands, f32 accumulate/state (BA f32)", "data": "synthetic", "config": workload_config(args.config, E),
+           "breakdown_ms": {"corr": corr_ms, "ba": ba_ms, "update_op_and_rest": ms - corr_ms - ba_ms, "gemm_backend": args.gemm},
+           "e2e": {"value": world * 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches), "clocks": clocks,
+           "roofline": {"kernel": "corr_fwd_mma (2-level patch correlation)", "bound": "hbm", "achieved": ach, "peak": hbm,
+                        "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": which,
+                        "algorithmic_bytes_per_launch": BYTES_PER_EDGE_FP16 * E, "kernel_ms": corr_ms}}
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        stride = 24 if args.config == "default" else 8
+        step, Es, Ef = cpu_reference_step_factory(args.config, stride, threads)
+        step()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            step()
+        full = (time.perf_counter() - t0) / reps * Ef / Es
+        out["cpu_baseline"] = {"value": 1.0 / full, "unit": "frames/s", "cores": threads, "kind": "port",
+                               "sample": "edges of every %dth patch (%d of %d edges), time scaled to the full graph" % (stride, Es, Ef)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="default", choices=["default", "fast"])
+    ap.add_argument("--gemm", default="cublas", choices=["cublas", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -387,3 +387,15 @@ extern "C" int dpvo_neighbors(const int64_t* ii, const int64_t* jj, int64_t E,
   DPVO_LAUNCH_CHECK("neighbors_kernel");
   return DPVO_OK;
 }
+
+extern "C" int dpvo_neighbors_from_groups(const int32_t* order, const int32_t* group_of, int64_t E,
+                                          int64_t* ix, int64_t* jx, void* stream) {
+  DPVO_REQUIRE(E >= 0, "neighbors_from_groups: negative E");
+  if (E == 0) return DPVO_OK;
+  DPVO_REQUIRE(order && group_of && ix && jx, "neighbors_from_groups: null pointer");
+  const int threads = 256;
+  const unsigned blocks = (unsigned)std::min<int64_t>((E + threads - 1) / threads, (int64_t)sm_count() * 8);
+  neighbors_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(order, group_of, E, ix, jx);
+  DPVO_LAUNCH_CHECK("neighbors_kernel");
+  return DPVO_OK;
+}

@@ -307,6 +307,121 @@ Tensor reproject_clamped(Tensor poses, Tensor patches, Tensor intrinsics, Tensor
   return reproject_impl(poses, patches, intrinsics, ii, jj, kk, 1);
 }
 
+
+// ---- update-operator building blocks (include/dpvo_b200.h, "Update operator building blocks")
+int dt16or32(const Tensor& t) {
+  TORCH_CHECK(t.scalar_type() == at::kHalf || t.scalar_type() == at::kFloat, "dpvo_b200: expected float16 or float32");
+  return dt(t);
+}
+
+std::vector<Tensor> add_layernorm(Tensor a, c10::optional<Tensor> b, c10::optional<Tensor> c, Tensor gamma, Tensor beta,
+                                  double eps, bool relu, bool want32, bool want16) {
+  need_cuda(a, "a");
+  c10::cuda::CUDAGuard guard(a.device());
+  const int dim = a.size(-1);
+  const int64_t rows = a.numel() / dim;
+  a = a.contiguous();
+  Tensor bb, cc;
+  int dts[3] = {dt16or32(a), 0, 0};
+  if (b.has_value()) { bb = b->contiguous(); dts[1] = dt16or32(bb); TORCH_CHECK(bb.numel() == a.numel(), "add_layernorm: shape mismatch"); }
+  if (c.has_value()) { cc = c->contiguous(); dts[2] = dt16or32(cc); TORCH_CHECK(cc.numel() == a.numel(), "add_layernorm: shape mismatch"); }
+  gamma = f32c(gamma); beta = f32c(beta);
+  Tensor y32, y16;
+  if (want32) y32 = torch::empty(a.sizes(), a.options().dtype(at::kFloat));
+  if (want16) y16 = torch::empty(a.sizes(), a.options().dtype(at::kHalf));
+  check(dpvo_add_layernorm(a.data_ptr(), bb.defined() ? bb.data_ptr() : nullptr, cc.defined() ? cc.data_ptr() : nullptr, dts,
+                           gamma.data_ptr<float>(), beta.data_ptr<float>(), (float)eps, want32 ? y32.data_ptr() : nullptr,
+                           want16 ? y16.data_ptr() : nullptr, relu ? 1 : 0, rows, dim, stream()),
+        "dpvo_b200_ext.add_layernorm");
+  return {y32, y16};
+}
+
+Tensor gather_rows_masked(Tensor x, Tensor idx, bool half_out) {
+  need_cuda(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  x = x.contiguous(); idx = i64c(idx);
+  const int dim = x.size(-1);
+  const int64_t rows = idx.numel();
+  Tensor y = torch::empty({1, rows, dim}, x.options().dtype(half_out ? at::kHalf : at::kFloat));
+  check(dpvo_gather_rows_masked(x.data_ptr(), dt16or32(x), idx.data_ptr<int64_t>(), y.data_ptr(), dt(y), rows, dim, stream()),
+        "dpvo_b200_ext.gather_rows_masked");
+  return y;
+}
+
+Tensor residual_add_(Tensor net32, Tensor u, c10::optional<Tensor> group_of, bool want16) {
+  need_cuda(net32, "net");
+  c10::cuda::CUDAGuard guard(net32.device());
+  TORCH_CHECK(net32.is_contiguous() && net32.scalar_type() == at::kFloat, "residual_add_: net must be contiguous float32");
+  u = u.contiguous();
+  const int dim = net32.size(-1);
+  const int64_t rows = net32.numel() / dim;
+  Tensor gof, n16;
+  if (group_of.has_value()) { gof = group_of->to(at::kInt).contiguous(); TORCH_CHECK(gof.numel() == rows, "residual_add_: group_of length"); }
+  else TORCH_CHECK(u.numel() == net32.numel(), "residual_add_: shape mismatch");
+  if (want16) n16 = torch::empty(net32.sizes(), net32.options().dtype(at::kHalf));
+  check(dpvo_residual_add(net32.data_ptr(), u.data_ptr(), dt16or32(u), gof.defined() ? gof.data_ptr<int>() : nullptr,
+                          want16 ? n16.data_ptr() : nullptr, rows, dim, stream()),
+        "dpvo_b200_ext.residual_add_");
+  return n16;
+}
+
+std::vector<Tensor> gated_residual(Tensor x32, Tensor gate16, Tensor res16, bool want_relu16) {
+  need_cuda(x32, "x");
+  c10::cuda::CUDAGuard guard(x32.device());
+  TORCH_CHECK(x32.scalar_type() == at::kFloat && gate16.scalar_type() == at::kHalf && res16.scalar_type() == at::kHalf,
+              "gated_residual: expects (float32, float16, float16)");
+  x32 = x32.contiguous(); gate16 = gate16.contiguous(); res16 = res16.contiguous();
+  const int dim = x32.size(-1);
+  const int64_t rows = x32.numel() / dim;
+  Tensor y = torch::empty_like(x32), r16;
+  if (want_relu16) r16 = torch::empty(x32.sizes(), x32.options().dtype(at::kHalf));
+  check(dpvo_gated_residual(x32.data_ptr(), gate16.data_ptr(), res16.data_ptr(), y.data_ptr(),
+                            want_relu16 ? r16.data_ptr() : nullptr, rows, dim, stream()),
+        "dpvo_b200_ext.gated_residual");
+  return {y, r16};
+}
+
+// fg: [.., E, 2*dim] fp16 = [f | g] (one GEMM with the f and g weights stacked)
+Tensor softagg_reduce(Tensor fg, Tensor order, Tensor group_start, Tensor n_groups, int64_t max_groups) {
+  need_cuda(fg, "fg");
+  c10::cuda::CUDAGuard guard(fg.device());
+  TORCH_CHECK(fg.scalar_type() == at::kHalf && fg.is_contiguous() && fg.size(-1) % 2 == 0, "softagg_reduce: expects contiguous float16 [E, 2*dim]");
+  const int dim = fg.size(-1) / 2;
+  Tensor y = torch::zeros({1, max_groups, dim}, fg.options());
+  const at::Half* base = fg.data_ptr<at::Half>();
+  check(dpvo_softagg_reduce(base, base + dim, 2 * dim, order.data_ptr<int>(), group_start.data_ptr<int>(),
+                            n_groups.data_ptr<int>(), max_groups, y.data_ptr(), dim, stream()),
+        "dpvo_b200_ext.softagg_reduce");
+  return y;
+}
+
+std::vector<Tensor> neighbors_from_groups(Tensor order, Tensor group_of) {
+  need_cuda(order, "order");
+  c10::cuda::CUDAGuard guard(order.device());
+  const int64_t E = order.numel();
+  auto ol = order.options().dtype(at::kLong);
+  Tensor ix = torch::empty({E}, ol), jx = torch::empty({E}, ol);
+  check(dpvo_neighbors_from_groups(order.data_ptr<int>(), group_of.data_ptr<int>(), E, ix.data_ptr<int64_t>(),
+                                   jx.data_ptr<int64_t>(), stream()),
+        "dpvo_b200_ext.neighbors_from_groups");
+  return {ix, jx};
+}
+
+std::vector<Tensor> update_heads(Tensor net32, Tensor W4, Tensor b4) {
+  need_cuda(net32, "net");
+  c10::cuda::CUDAGuard guard(net32.device());
+  TORCH_CHECK(net32.scalar_type() == at::kFloat, "update_heads: net must be float32");
+  net32 = net32.contiguous(); W4 = f32c(W4); b4 = f32c(b4);
+  const int dim = net32.size(-1);
+  const int64_t rows = net32.numel() / dim;
+  TORCH_CHECK(W4.numel() == 4 * dim && b4.numel() == 4, "update_heads: W4 [4,dim], b4 [4]");
+  Tensor delta = torch::empty({1, rows, 2}, net32.options()), weight = torch::empty({1, rows, 2}, net32.options());
+  check(dpvo_update_heads(net32.data_ptr(), W4.data_ptr<float>(), b4.data_ptr<float>(), delta.data_ptr<float>(),
+                          weight.data_ptr<float>(), rows, dim, stream()),
+        "dpvo_b200_ext.update_heads");
+  return {delta, weight};
+}
+
 int64_t launch_count() { return dpvo_launch_count(); }
 std::string version() { return dpvo_version(); }
 
@@ -353,6 +468,13 @@ PYBIND11_MODULE(dpvo_b200_ext, m) {
   m.def("group_edges", &group_edges, "device edge grouping", py::arg("key_a"), py::arg("key_b") = py::none(),
         py::arg("sec") = py::none());
   m.def("reproject_clamped", &reproject_clamped, "pops.transform-compatible fused reprojection");
+  m.def("add_layernorm", &add_layernorm, "fused add + LayerNorm (+ReLU)");
+  m.def("gather_rows_masked", &gather_rows_masked, "masked row gather");
+  m.def("residual_add_", &residual_add_, "in-place residual add with optional row indirection");
+  m.def("gated_residual", &gated_residual, "x + sigmoid(g) * r");
+  m.def("softagg_reduce", &softagg_reduce, "segment softmax-weighted sum");
+  m.def("update_heads", &update_heads, "delta / weight heads");
+  m.def("neighbors_from_groups", &neighbors_from_groups, "temporal neighbours from a kk/jj grouping");
   m.def("launch_count", &launch_count, "kernel launches issued by libdpvo_b200 so far");
   m.def("version", &version, "library version string");
 }

@@ -1,0 +1,264 @@
+// Row-wise building blocks of the update operator (dpvo/net.py:74-92, dpvo/blocks.py:15-48).
+//
+// Everything that is not a dense layer is HBM-bound row streaming over [E, 384] activations, so
+// each kernel here fuses a whole elementwise/normalisation group into ONE pass: one warp per row,
+// 16-byte accesses, fp32 statistics, and -- where the next consumer is a tensor-core GEMM -- an fp16
+// copy written in the same pass so the GEMM never re-reads fp32.
+//
+//   add_layernorm        y = LN(a + b + c) * gamma + beta (+ReLU)       net.py:77-78, 46-51, 53-60
+//   gather_rows_masked   y[e] = idx[e] >= 0 ? x[idx[e]] : 0             net.py:81-85
+//   residual_add         net += u                                        net.py:84-85
+//   softagg_reduce       segment softmax-weighted sum                    blocks.py:40-43 (torch_scatter)
+//   scatter_add_rows     net += h[group_of[e]]                           blocks.py:45-46 + net.py:87-88
+//   gated_residual       x + sigmoid(g) * r                              blocks.py:28-29
+//   heads                delta = Wd relu(net), weight = sigmoid(Ww relu(net))   net.py:62-71, 92
+#include "common.cuh"
+
+namespace dpvo {
+
+// ---- 4-wide typed row access ---------------------------------------------------------------
+__device__ __forceinline__ float4 load4(const void* base, int dtype, int64_t elem) {
+  if (dtype == DPVO_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
+  const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + elem);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store4(void* base, int dtype, int64_t elem, float4 v) {
+  if (dtype == DPVO_F32) { *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem) = v; return; }
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 q; q.x = *reinterpret_cast<uint32_t*>(&a); q.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(base) + elem) = q;
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+constexpr int ROW_WARPS = 8;
+constexpr int MAX_V4 = 8;     // up to 8 float4 per lane -> dim <= 1024
+
+// ---- add + LayerNorm ------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+add_layernorm_kernel(const void* a, const void* b, const void* c, int da, int db, int dc,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     float* y32, __half* y16, int relu, int64_t rows, int dim) {
+  const int lane = threadIdx.x & 31;
+  const int nv = dim >> 7;    // float4 per lane (dim % 128 == 0)
+  for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * ROW_WARPS) {
+    float4 v[MAX_V4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i) {
+      if (i < nv) {
+        const int64_t e = r * dim + (i * 32 + lane) * 4;
+        float4 t = load4(a, da, e);
+        if (b) t = add4(t, load4(b, db, e));
+        if (c) t = add4(t, load4(c, dc, e));
+        v[i] = t;
+        s += (t.x + t.y) + (t.z + t.w);
+      }
+    }
+    const float mean = warp_sum(s) / (float)dim;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i) {
+      if (i < nv) {
+        const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)dim + eps);
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i) {
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+        const float4 bt = *reinterpret_cast<const float4*>(beta + col);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + bt.x;
+        o.y = (v[i].y - mean) * rstd * g.y + bt.y;
+        o.z = (v[i].z - mean) * rstd * g.z + bt.z;
+        o.w = (v[i].w - mean) * rstd * g.w + bt.w;
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (y32) store4(y32, DPVO_F32, r * dim + col, o);
+        if (y16) store4(y16, DPVO_F16, r * dim + col, o);
+      }
+    }
+  }
+}
+
+// ---- gather / residual / scatter / gate -------------------------------------------------------
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+gather_rows_masked_kernel(const void* x, int dx, const int64_t* __restrict__ idx, void* y, int dy, int64_t rows, int dim) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * ROW_WARPS) {
+    const int64_t src = idx[r];
+    for (int col = lane * 4; col < dim; col += 128) {
+      const float4 v = (src >= 0) ? load4(x, dx, src * dim + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      store4(y, dy, r * dim + col, v);
+    }
+  }
+}
+
+// net32[r] += u[src(r)]   (src = r, or group_of[r]);  optional fp16 copy of the result
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+residual_add_kernel(float* net, const void* u, int du, const int32_t* __restrict__ group_of, __half* net16,
+                    int64_t rows, int dim) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * ROW_WARPS) {
+    const int64_t src = group_of ? (int64_t)group_of[r] : r;
+    for (int col = lane * 4; col < dim; col += 128) {
+      const float4 v = add4(load4(net, DPVO_F32, r * dim + col), load4(u, du, src * dim + col));
+      store4(net, DPVO_F32, r * dim + col, v);
+      if (net16) store4(net16, DPVO_F16, r * dim + col, v);
+    }
+  }
+}
+
+// y = x + sigmoid(g) * res ; optional relu'd fp16 copy (input of the two heads)
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+gated_residual_kernel(const float* x, const __half* g, const __half* res, float* y32, __half* y16_relu,
+                      int64_t rows, int dim) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * ROW_WARPS) {
+    for (int col = lane * 4; col < dim; col += 128) {
+      const int64_t e = r * dim + col;
+      const float4 xv = load4(x, DPVO_F32, e), gv = load4(g, DPVO_F16, e), rv = load4(res, DPVO_F16, e);
+      float4 o;
+      o.x = xv.x + sigmoidf_(gv.x) * rv.x; o.y = xv.y + sigmoidf_(gv.y) * rv.y;
+      o.z = xv.z + sigmoidf_(gv.z) * rv.z; o.w = xv.w + sigmoidf_(gv.w) * rv.w;
+      store4(y32, DPVO_F32, e, o);
+      if (y16_relu) store4(y16_relu, DPVO_F16, e, make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f)));
+    }
+  }
+}
+
+// ---- SoftAgg: one CTA per group, one thread per 2 channels, single pass online softmax --------
+__global__ void __launch_bounds__(256)
+softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ gl, int64_t ld,
+                      const int32_t* __restrict__ order,
+                      const int32_t* __restrict__ group_start, const int32_t* __restrict__ n_groups,
+                      __half* __restrict__ y, int dim) {
+  const int G = *n_groups;
+  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    const int s = group_start[g], e = group_start[g + 1];
+    for (int col = threadIdx.x * 2; col < dim; col += blockDim.x * 2) {
+      float m0 = -INFINITY, m1 = -INFINITY, z0 = 0.f, z1 = 0.f, a0 = 0.f, a1 = 0.f;
+      for (int k = s; k < e; ++k) {
+        const int64_t row = (int64_t)order[k] * ld + col;
+        const float2 gv = __half22float2(*reinterpret_cast<const __half2*>(gl + row));
+        const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(f + row));
+        if (gv.x > m0) { const float sc = __expf(m0 - gv.x); z0 *= sc; a0 *= sc; m0 = gv.x; }
+        if (gv.y > m1) { const float sc = __expf(m1 - gv.y); z1 *= sc; a1 *= sc; m1 = gv.y; }
+        const float w0 = __expf(gv.x - m0), w1 = __expf(gv.y - m1);
+        z0 += w0; a0 += w0 * fv.x;
+        z1 += w1; a1 += w1 * fv.y;
+      }
+      *reinterpret_cast<__half2*>(y + (int64_t)g * dim + col) = __floats2half2_rn(a0 / z0, a1 / z1);
+    }
+  }
+}
+
+// ---- heads: out[r] = (Wd relu(net[r]) + bd, sigmoid(Ww relu(net[r]) + bw)) ---------------------
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+heads_kernel(const float* __restrict__ net, const float* __restrict__ W4, const float* __restrict__ b4,
+             float* __restrict__ delta, float* __restrict__ weight, int64_t rows, int dim) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * ROW_WARPS) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int col = lane * 4; col < dim; col += 128) {
+      float4 x = load4(net, DPVO_F32, r * dim + col);
+      x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const float4 w = *reinterpret_cast<const float4*>(W4 + o * dim + col);
+        acc[o] += (x.x * w.x + x.y * w.y) + (x.z * w.z + x.w * w.w);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
+    if (lane == 0) {
+      delta[r * 2 + 0] = acc[0] + b4[0];
+      delta[r * 2 + 1] = acc[1] + b4[1];
+      weight[r * 2 + 0] = sigmoidf_(acc[2] + b4[2]);
+      weight[r * 2 + 1] = sigmoidf_(acc[3] + b4[3]);
+    }
+  }
+}
+
+static inline unsigned row_grid(int64_t rows) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + ROW_WARPS - 1) / ROW_WARPS, (int64_t)sm_count() * 8));
+}
+static inline bool ok_dt(int d) { return d == DPVO_F16 || d == DPVO_F32; }
+
+}  // namespace dpvo
+
+using namespace dpvo;
+
+extern "C" int dpvo_add_layernorm(const void* a, const void* b, const void* c, const int* in_dtypes,
+                                  const float* gamma, const float* beta, float eps,
+                                  void* y32, void* y16, int relu, int64_t rows, int dim, void* stream) {
+  DPVO_REQUIRE(rows >= 0 && dim > 0, "add_layernorm: bad sizes");
+  if (rows == 0) return DPVO_OK;
+  DPVO_REQUIRE(a && in_dtypes && gamma && beta && (y32 || y16), "add_layernorm: null pointer");
+  DPVO_REQUIRE(dim % 128 == 0 && dim <= 128 * MAX_V4, "add_layernorm: dim must be a multiple of 128, <= %d", 128 * MAX_V4);
+  DPVO_REQUIRE(ok_dt(in_dtypes[0]) && (!b || ok_dt(in_dtypes[1])) && (!c || ok_dt(in_dtypes[2])), "add_layernorm: dtype");
+  add_layernorm_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      a, b, c, in_dtypes[0], b ? in_dtypes[1] : 0, c ? in_dtypes[2] : 0, gamma, beta, eps, (float*)y32, (__half*)y16, relu, rows, dim);
+  DPVO_LAUNCH_CHECK("add_layernorm_kernel");
+  return DPVO_OK;
+}
+
+extern "C" int dpvo_gather_rows_masked(const void* x, int x_dtype, const int64_t* idx,
+                                       void* y, int y_dtype, int64_t rows, int dim, void* stream) {
+  DPVO_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0, "gather_rows_masked: bad sizes");
+  if (rows == 0) return DPVO_OK;
+  DPVO_REQUIRE(x && idx && y && ok_dt(x_dtype) && ok_dt(y_dtype), "gather_rows_masked: bad argument");
+  gather_rows_masked_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(x, x_dtype, idx, y, y_dtype, rows, dim);
+  DPVO_LAUNCH_CHECK("gather_rows_masked_kernel");
+  return DPVO_OK;
+}
+
+extern "C" int dpvo_residual_add(void* net32, const void* u, int u_dtype, const int32_t* group_of, void* net16,
+                                 int64_t rows, int dim, void* stream) {
+  DPVO_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0, "residual_add: bad sizes");
+  if (rows == 0) return DPVO_OK;
+  DPVO_REQUIRE(net32 && u && ok_dt(u_dtype), "residual_add: bad argument");
+  residual_add_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>((float*)net32, u, u_dtype, group_of, (__half*)net16, rows, dim);
+  DPVO_LAUNCH_CHECK("residual_add_kernel");
+  return DPVO_OK;
+}
+
+extern "C" int dpvo_gated_residual(const void* x32, const void* gate16, const void* res16, void* y32, void* y16_relu,
+                                   int64_t rows, int dim, void* stream) {
+  DPVO_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0, "gated_residual: bad sizes");
+  if (rows == 0) return DPVO_OK;
+  DPVO_REQUIRE(x32 && gate16 && res16 && y32, "gated_residual: null pointer");
+  gated_residual_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      (const float*)x32, (const __half*)gate16, (const __half*)res16, (float*)y32, (__half*)y16_relu, rows, dim);
+  DPVO_LAUNCH_CHECK("gated_residual_kernel");
+  return DPVO_OK;
+}
+
+extern "C" int dpvo_softagg_reduce(const void* f16, const void* g16, int64_t ld, const int32_t* order, const int32_t* group_start,
+                                   const int32_t* n_groups, int64_t max_groups, void* y16, int dim, void* stream) {
+  DPVO_REQUIRE(max_groups >= 0 && dim > 0 && dim % 2 == 0, "softagg_reduce: bad sizes");
+  if (max_groups == 0) return DPVO_OK;
+  DPVO_REQUIRE(f16 && g16 && order && group_start && n_groups && y16, "softagg_reduce: null pointer");
+  DPVO_REQUIRE(ld >= dim && ld % 2 == 0, "softagg_reduce: row stride must be even and >= dim");
+  const unsigned grid = (unsigned)std::min<int64_t>(max_groups, (int64_t)sm_count() * 8);
+  const int threads = std::min(256, std::max(32, ((dim / 2 + 31) / 32) * 32));
+  softagg_reduce_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)f16, (const __half*)g16, ld, order, group_start,
+                                                                   n_groups, (__half*)y16, dim);
+  DPVO_LAUNCH_CHECK("softagg_reduce_kernel");
+  return DPVO_OK;
+}
+
+extern "C" int dpvo_update_heads(const void* net32, const float* W4, const float* b4, float* delta, float* weight,
+                                 int64_t rows, int dim, void* stream) {
+  DPVO_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0, "update_heads: bad sizes");
+  if (rows == 0) return DPVO_OK;
+  DPVO_REQUIRE(net32 && W4 && b4 && delta && weight, "update_heads: null pointer");
+  heads_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>((const float*)net32, W4, b4, delta, weight, rows, dim);
+  DPVO_LAUNCH_CHECK("heads_kernel");
+  return DPVO_OK;
+}

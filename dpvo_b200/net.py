@@ -1,0 +1,160 @@
+"""The recurrent update operator (dpvo/net.py:27-92, dpvo/blocks.py:15-48) on sm_100a kernels.
+
+`Update` keeps the reference's sub-module names, so a DPVO checkpoint's "update.*" state_dict keys
+load unchanged (update.c1.0.weight, update.agg_kk.f.weight, update.gru.1.gate.0.weight, ...).
+
+Inference forward = 17 dense layers + fused row kernels:
+    corr MLP 882->384->384->LN->384 | LN(net+inp+.) | c1,c2 on masked temporal neighbours |
+    SoftAgg over patches (kk) and over frame pairs (ii,jj) | 2x (LN, gated residual) | heads
+Data flow is fp32 for the carried state `net`, fp16 for every GEMM operand (what the reference's
+autocast does, dpvo.py:332), with the fp16 copies produced inside the fused row kernels.  The edge
+groupings come from ONE device radix-sort launch each (no host sync, no torch.unique, no D2H sort).
+
+Dense layers go through `dense()`: the tcgen05 kernel of include/dpvo_b200.h (dpvo_linear_f16) when
+`gemm="tcgen05"`, or cuBLAS via torch (`gemm="cublas"`, the library baseline kept for comparison).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import extensions
+
+DIM = 384
+
+
+class GradClip(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        g = torch.where(torch.isnan(g), torch.zeros_like(g), g)
+        return g.clamp(min=-0.01, max=0.01)
+
+
+class GradientClip(nn.Module):
+    def forward(self, x):
+        return GradClip.apply(x)
+
+
+class GatedResidual(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.gate = nn.Sequential(nn.Linear(dim, dim), nn.Sigmoid())
+        self.res = nn.Sequential(nn.Linear(dim, dim), nn.ReLU(inplace=True), nn.Linear(dim, dim))
+
+    def forward(self, x):
+        return x + self.gate(x) * self.res(x)
+
+
+class SoftAgg(nn.Module):
+    """Parameters only; the reduction runs in dpvo_softagg_reduce."""
+
+    def __init__(self, dim=512, expand=True):
+        super().__init__()
+        self.dim, self.expand = dim, expand
+        self.f = nn.Linear(dim, dim)
+        self.g = nn.Linear(dim, dim)
+        self.h = nn.Linear(dim, dim)
+
+
+class EdgeGroups:
+    """Device-resident CSR of an edge grouping (dpvo_group_edges); G bounds are host hints."""
+
+    def __init__(self, key_a, key_b=None, sec=None, max_groups=None):
+        ex = extensions()[3]
+        self.order, self.group_of, self.group_start, self.key_a, self.key_b, self.n = ex.group_edges(key_a, key_b, sec)
+        self.max_groups = int(self.n.item()) if max_groups is None else int(max_groups)
+
+
+class Update(nn.Module):
+    def __init__(self, p=3, gemm="cublas"):
+        super().__init__()
+        self.c1 = nn.Sequential(nn.Linear(DIM, DIM), nn.ReLU(inplace=True), nn.Linear(DIM, DIM))
+        self.c2 = nn.Sequential(nn.Linear(DIM, DIM), nn.ReLU(inplace=True), nn.Linear(DIM, DIM))
+        self.norm = nn.LayerNorm(DIM, eps=1e-3)
+        self.agg_kk = SoftAgg(DIM)
+        self.agg_ij = SoftAgg(DIM)
+        self.gru = nn.Sequential(nn.LayerNorm(DIM, eps=1e-3), GatedResidual(DIM),
+                                 nn.LayerNorm(DIM, eps=1e-3), GatedResidual(DIM))
+        self.corr = nn.Sequential(nn.Linear(2 * 49 * p * p, DIM), nn.ReLU(inplace=True), nn.Linear(DIM, DIM),
+                                  nn.LayerNorm(DIM, eps=1e-3), nn.ReLU(inplace=True), nn.Linear(DIM, DIM))
+        self.d = nn.Sequential(nn.ReLU(inplace=False), nn.Linear(DIM, 2), GradientClip())
+        self.w = nn.Sequential(nn.ReLU(inplace=False), nn.Linear(DIM, 2), GradientClip(), nn.Sigmoid())
+        self.gemm = gemm
+        self._packed = None
+
+    # ------------------------------------------------------------------ packed inference weights
+    def pack(self):
+        """fp16 copies of the dense weights (+ fp32 biases) for the inference path; call again after
+        loading a checkpoint."""
+        def lin(m):
+            return (m.weight.detach().half().contiguous(), m.bias.detach().float().contiguous())
+        P = {}
+        P["corr0"], P["corr2"], P["corr5"] = lin(self.corr[0]), lin(self.corr[2]), lin(self.corr[5])
+        P["c1a"], P["c1b"], P["c2a"], P["c2b"] = lin(self.c1[0]), lin(self.c1[2]), lin(self.c2[0]), lin(self.c2[2])
+        for nm, agg in (("kk", self.agg_kk), ("ij", self.agg_ij)):
+            # f and g share their input: one GEMM with N = 768
+            P["fg_" + nm] = (torch.cat([agg.f.weight, agg.g.weight], 0).detach().half().contiguous(),
+                             torch.cat([agg.f.bias, agg.g.bias], 0).detach().float().contiguous())
+            P["h_" + nm] = lin(agg.h)
+        for i, blk in ((1, self.gru[1]), (3, self.gru[3])):
+            P["gr%d_g" % i], P["gr%d_a" % i], P["gr%d_b" % i] = lin(blk.gate[0]), lin(blk.res[0]), lin(blk.res[2])
+        P["heads_w"] = torch.cat([self.d[1].weight, self.w[1].weight], 0).detach().float().contiguous()
+        P["heads_b"] = torch.cat([self.d[1].bias, self.w[1].bias], 0).detach().float().contiguous()
+        self._packed = P
+        return P
+
+    def dense(self, x16, wb, relu=False):
+        w, b = wb
+        if self.gemm == "cublas":
+            y = F.linear(x16, w, b.half())
+            return F.relu_(y) if relu else y
+        raise RuntimeError("Update: unknown gemm backend %r" % self.gemm)
+
+    # ------------------------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward(self, net, inp, corr, flow, ii, jj, kk, groups_kk=None, groups_ij=None):
+        """net [1,E,384] (fp16 or fp32), inp [1,E,384], corr [1,E,882], ii/jj/kk int64 [E].
+        Returns (net fp32, (delta [1,E,2], weight [1,E,2], None)) like net.py:92."""
+        ex = extensions()[3]
+        P = self._packed or self.pack()
+        E = net.shape[1]
+        corr = corr.half() if corr.dtype != torch.half else corr
+        inp = inp.half() if inp.dtype not in (torch.half, torch.float32) else inp
+
+        # corr MLP (net.py:53-60) and the first LayerNorm (:77-78)
+        h = self.dense(corr, P["corr0"], relu=True)
+        h = self.dense(h, P["corr2"])
+        _, h = ex.add_layernorm(h, None, None, self.corr[3].weight, self.corr[3].bias, 1e-3, True, False, True)
+        h = self.dense(h, P["corr5"])
+        net32, _ = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, False)
+
+        # temporal neighbours of every edge along its patch track (net.py:80-85)
+        if groups_kk is None:
+            groups_kk = EdgeGroups(kk, None, jj)
+        ix, jx = ex.neighbors_from_groups(groups_kk.order, groups_kk.group_of)
+        for idx, a, b in ((ix, "c1a", "c1b"), (jx, "c2a", "c2b")):
+            g16 = ex.gather_rows_masked(net32, idx, True)
+            u = self.dense(self.dense(g16, P[a], relu=True), P[b])
+            n16 = ex.residual_add_(net32, u, None, idx is jx)
+
+        # soft aggregation over patches, then over frame pairs (net.py:87-88, blocks.py:40-48)
+        if groups_ij is None:
+            groups_ij = EdgeGroups(ii, jj, None)
+        for grp, nm in ((groups_kk, "kk"), (groups_ij, "ij")):
+            fg = self.dense(n16, P["fg_" + nm])
+            y = ex.softagg_reduce(fg, grp.order, grp.group_start, grp.n, grp.max_groups)
+            hy = self.dense(y, P["h_" + nm])
+            n16 = ex.residual_add_(net32, hy, grp.group_of, True)
+
+        # 2 x (LayerNorm, gated residual) (net.py:46-51, blocks.py:28-29)
+        x32 = net32
+        for i, ln in ((1, self.gru[0]), (3, self.gru[2])):
+            x32, x16 = ex.add_layernorm(x32, None, None, ln.weight, ln.bias, 1e-3, False, True, True)
+            gate = self.dense(x16, P["gr%d_g" % i])
+            r2 = self.dense(self.dense(x16, P["gr%d_a" % i], relu=True), P["gr%d_b" % i])
+            x32, _ = ex.gated_residual(x32, gate, r2, False)
+        delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"])
+        return x32, (delta, weight, None)

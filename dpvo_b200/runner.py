@@ -1,0 +1,111 @@
+"""One DPVO `update()` iteration on the sm_100a kernels -- the public call a user makes.
+
+Mirrors DPVO.update (dpvo/dpvo.py:328-360):
+    reproject -> correlation (2 levels) -> context gather -> update operator -> target/weight ->
+    2 Gauss-Newton bundle-adjustment iterations
+over state tensors laid out like dpvo/dpvo.py:58-73 / dpvo/patchgraph.py:26-35.  `ingest_frame`
+is the per-frame host->device traffic of DPVO.__call__ (dpvo.py:426-438): the new frame's feature
+maps, patch features and patches copied from pinned host memory into their ring-buffer slots.
+"""
+import torch
+
+from . import extensions
+from . import altcorr, fastba
+from . import projective_ops as pops
+from .net import Update, EdgeGroups, DIM
+
+
+class UpdateRunner:
+    def __init__(self, state, update=None, gemm="cublas", ba_iterations=2, seed=1234):
+        self.s = state
+        dev = state.poses.device
+        if update is None:
+            torch.manual_seed(seed)                    # evaluate_tartan.py:173
+            update = Update(3, gemm=gemm)
+        self.update = update.to(dev).eval()
+        self.update.gemm = gemm
+        self.update.pack()
+        self.M = state.cfg["M"]
+        self.mem = state.fmap1.shape[1]
+        self.pmem = state.imap.shape[1] // self.M
+        self.ba_iterations = ba_iterations
+        self.lmbda = torch.as_tensor([1e-4], device=dev)
+        self.poses0 = state.poses.clone()
+        self.patches0 = state.patches.clone()
+        self.net = torch.zeros(1, state.E, DIM, device=dev, dtype=torch.float32)
+        self.timers = None
+        # host-known bounds on the number of groups (no device->host sync in the step)
+        n_live_frames = int((state.kk // self.M).unique().numel())
+        self.max_patch_groups = n_live_frames * self.M
+        self.max_pair_groups = int(torch.unique(state.ii * 100000 + state.jj).numel())
+        self.kk_ring = state.kk % (self.M * self.pmem)
+        self.jj_ring = state.jj % self.mem
+
+    def reset(self):
+        self.s.poses.copy_(self.poses0)
+        self.s.patches.copy_(self.patches0)
+
+    # -------------------------------------------------------------------------------- one update
+    @torch.no_grad()
+    def step(self):
+        s = self.s
+        ev = self.timers
+        poses = s.poses.view(1, -1, 7)
+        patches = s.patches.view(1, -1, 3, 3, 3)
+        intr = s.intrinsics.view(1, -1, 4)
+        coords = pops.transform_fused(poses, patches, intr, s.ii, s.jj, s.kk)               # [1,E,2,3,3]
+        if ev is not None:
+            ev["corr0"].record()
+        corr = altcorr.corr_pyramid(s.gmap, (s.fmap1, s.fmap2), coords, self.kk_ring, self.jj_ring, 3, 4.0)
+        if ev is not None:
+            ev["corr1"].record()
+        ctx = s.imap[:, self.kk_ring]
+        groups_kk = EdgeGroups(s.kk, None, s.jj, max_groups=self.max_patch_groups)
+        groups_ij = EdgeGroups(s.ii, s.jj, None, max_groups=self.max_pair_groups)
+        self.net, (delta, weight, _) = self.update(self.net, ctx, corr, None, s.ii, s.jj, s.kk, groups_kk, groups_ij)
+        target = coords[:, :, :, 1, 1] + delta
+        if ev is not None:
+            ev["ba0"].record()
+        fastba.BA(poses, patches, intr, target, weight, self.lmbda, s.ii, s.jj, s.kk, s.t0, s.n, self.M,
+                  self.ba_iterations, False)
+        if ev is not None:
+            ev["ba1"].record()
+        return target, weight
+
+    # ----------------------------------------------------------------- end to end (host buffers)
+    def make_host_frame(self, seed=0):
+        """pinned host copies of everything DPVO.__call__ writes for one new frame"""
+        s = self.s
+        g = torch.Generator().manual_seed(seed)
+        h, w = s.fmap1.shape[3], s.fmap1.shape[4]
+        f = dict(
+            fmap1=(torch.randn(h, w, 128, generator=g) / 4).half(),
+            fmap2=(torch.randn(h // 4, w // 4, 128, generator=g) / 4).half(),
+            gmap=(torch.randn(self.M, 3, 3, 128, generator=g) / 4).half(),
+            imap=(torch.randn(self.M, DIM, generator=g) / 4).half(),
+            patches=s.patches[(s.n - 1) * self.M:s.n * self.M].cpu().clone(),
+            pose=s.poses[s.n - 1].cpu().clone(),
+        )
+        return {k: v.pin_memory() for k, v in f.items()}
+
+    def ingest_frame(self, hf):
+        """H2D of one frame into ring slot n-1 (channels-last buffers take the host layout as is)."""
+        s = self.s
+        slot = (s.n - 1) % self.mem
+        pslot = (s.n - 1) % self.pmem
+        s.fmap1[0, slot].permute(1, 2, 0).copy_(hf["fmap1"], non_blocking=True)
+        s.fmap2[0, slot].permute(1, 2, 0).copy_(hf["fmap2"], non_blocking=True)
+        s.gmap[0, pslot * self.M:(pslot + 1) * self.M].permute(0, 2, 3, 1).copy_(hf["gmap"], non_blocking=True)
+        s.imap[0, pslot * self.M:(pslot + 1) * self.M].copy_(hf["imap"], non_blocking=True)
+        s.patches[(s.n - 1) * self.M:s.n * self.M].copy_(hf["patches"], non_blocking=True)
+        s.poses[s.n - 1].copy_(hf["pose"], non_blocking=True)
+        return sum(v.numel() * v.element_size() for v in hf.values())
+
+    def step_e2e(self, hf, out_poses, out_depth):
+        """ingest a frame from pinned host memory, update, read poses + patch depths back to host"""
+        s = self.s
+        h2d = self.ingest_frame(hf)
+        self.step()
+        out_poses.copy_(s.poses[:s.n], non_blocking=True)
+        out_depth.copy_(s.patches[:s.n * self.M, 2, 1, 1], non_blocking=True)
+        return h2d, out_poses.numel() * 4 + out_depth.numel() * 4

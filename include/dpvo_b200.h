@@ -156,6 +156,13 @@ int dpvo_group_edges(const int64_t* key_a, const int64_t* key_b, const int64_t* 
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * neighbors from an existing grouping keyed by the edge's patch and ordered by target frame
+ * (dpvo_group_edges(kk, NULL, jj, ...)): ix/jx = previous/next edge of the same group, -1 at ends.
+ */
+int dpvo_neighbors_from_groups(const int32_t* order, const int32_t* group_of, int64_t E,
+                               int64_t* ix, int64_t* jx, void* stream);
+
+/*
  * cuda_ba.neighbors -- ba.cpp:59-97.  For every edge e: ix[e] = the edge preceding e and
  * jx[e] = the edge following e among the edges with the same ii value, ordered by
  * (jj, original position) (std::stable_sort semantics); -1 at the ends.  int64 outputs.
@@ -248,38 +255,47 @@ int dpvo_lie_jinv(int group, int dtype, const void* X, const void* a, void* b, i
  * ====================================================================================== */
 
 /*
- * y[r, :] = LayerNorm(a[r] + b[r] + c[r]) * gamma + beta   (b, c optional, may be NULL)
- * rows x dim, eps as given (1e-3 in Update: net.py:41,47,49,57).  a/b/c dtype in_dtype
- * (per-tensor: in_dtypes[3]), y dtype out_dtype; gamma/beta fp32.  Statistics in fp32.
+ * y[r, :] = LayerNorm(a[r] + b[r] + c[r]) * gamma + beta, optionally followed by ReLU
+ * (b, c optional, may be NULL).  rows x dim, dim % 128 == 0, dim <= 1024; eps as given (1e-3 in
+ * Update: net.py:41,47,49,57).  a/b/c element types in_dtypes[3] (F16/F32); gamma/beta fp32;
+ * statistics in fp32.  Result written as fp32 (y32) and/or fp16 (y16) in the same pass.
  */
 int dpvo_add_layernorm(const void* a, const void* b, const void* c, const int* in_dtypes,
                        const float* gamma, const float* beta, float eps,
-                       void* y, int out_dtype, int64_t rows, int dim, void* stream);
+                       void* y32, void* y16, int relu, int64_t rows, int dim, void* stream);
 
-/*
- * Neighbour gather with mask (net.py:81-85): y[e, :] = (idx[e] >= 0) ? x[idx[e], :] : 0.
- */
+/* Neighbour gather with mask (net.py:81-85): y[e, :] = (idx[e] >= 0) ? x[idx[e], :] : 0. */
 int dpvo_gather_rows_masked(const void* x, int x_dtype, const int64_t* idx,
                             void* y, int y_dtype, int64_t rows, int dim, void* stream);
 
 /*
- * SoftAgg reduction (blocks.py:40-43, torch_scatter 2.1.2 scatter_softmax + scatter_sum):
- *   y[g, c] = sum_{e in group g} f[e, c] * exp(gl[e, c] - max_g) / sum_{e in g} exp(gl[e,c]-max_g)
- * using the CSR from dpvo_group_edges (order, group_start, G groups).  f, gl: [E, dim]
- * dtype in_dtype; y: [G, dim] dtype out_dtype.  G is read from n_groups (device) and y rows
- * beyond G are untouched; max_groups bounds the launch.
+ * net32[e, :] += u[src(e), :] with src(e) = e (group_of == NULL; residual adds of net.py:84-85)
+ * or src(e) = group_of[e] (the `[:, jx]` expand of blocks.py:46 fused with net.py:87-88).
+ * net32 fp32 in place; optional fp16 copy of the result in net16.
  */
-int dpvo_softagg_reduce(const void* f, const void* gl, int in_dtype,
-                        const int32_t* order, const int32_t* group_start,
-                        const int32_t* n_groups, int64_t max_groups,
-                        void* y, int out_dtype, int dim, void* stream);
+int dpvo_residual_add(void* net32, const void* u, int u_dtype, const int32_t* group_of, void* net16,
+                      int64_t rows, int dim, void* stream);
+
+/* GatedResidual (blocks.py:28-29): y32 = x32 + sigmoid(gate16) * res16; optional relu(y) as fp16. */
+int dpvo_gated_residual(const void* x32, const void* gate16, const void* res16, void* y32, void* y16_relu,
+                        int64_t rows, int dim, void* stream);
 
 /*
- * net[e, :] += h[group_of[e], :]   (the `[:, jx]` expand of blocks.py:46 fused with the
- * residual add of net.py:87-88).  net fp32 or fp16 in place.
+ * SoftAgg reduction (blocks.py:40-43; torch_scatter 2.1.2 scatter_softmax + scatter_sum):
+ *   y[g, c] = sum_{e in g} f[e, c] * exp(gl[e, c] - max_g) / sum_{e in g} exp(gl[e, c] - max_g)
+ * over the CSR of dpvo_group_edges (order, group_start; G read from n_groups on the device).
+ * f, gl fp16 [E, dim] with row stride ld elements (so both may be column blocks of one [E, 2*dim]
+ * GEMM output); y fp16 [G, dim]; max_groups bounds the launch.  fp32 math, one pass.
  */
-int dpvo_scatter_add_rows(void* net, int net_dtype, const void* h, int h_dtype,
-                          const int32_t* group_of, int64_t rows, int dim, void* stream);
+int dpvo_softagg_reduce(const void* f16, const void* g16, int64_t ld, const int32_t* order, const int32_t* group_start,
+                        const int32_t* n_groups, int64_t max_groups, void* y16, int dim, void* stream);
+
+/*
+ * The two output heads (net.py:62-71, 92): delta = Wd relu(net) + bd, weight = sigmoid(Ww relu(net) + bw).
+ * W4 fp32 [4, dim] = rows (Wd[0], Wd[1], Ww[0], Ww[1]); b4 fp32 [4]; delta, weight fp32 [rows, 2].
+ */
+int dpvo_update_heads(const void* net32, const float* W4, const float* b4, float* delta, float* weight,
+                      int64_t rows, int dim, void* stream);
 
 /*
  * Dense layer on tensor cores (tcgen05, fp16 operands, fp32 accumulate in TMEM):

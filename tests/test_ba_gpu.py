@@ -1,0 +1,120 @@
+"""cuda_ba.forward / reproject on the device vs the fp64 CPU oracle.  north_star bar: poses and
+inverse depths within 1e-4 relative."""
+import pytest
+import torch
+
+from oracle import ba as OB
+from dpvo_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _problem(config, n_frames, seed, sigma=1.0):
+    st = synthetic.make_state(config, n_frames, device="cpu", features=False, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    P = 3
+    coords = OB.fastba_reproject(st.poses.double(), st.patches.double(), st.intrinsics.double(), st.ii, st.jj, st.kk)
+    target = (coords[:, :, 1, 1] + sigma * torch.randn(st.E, 2, generator=g).double()).float()
+    weight = torch.rand(st.E, 2, generator=g)
+    return st, target, weight
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-12)).item()
+
+
+@pytest.mark.parametrize("config,n_frames,iters", [("fast", 12, 1), ("fast", 30, 2), ("default", 36, 2)])
+def test_ba_forward_matches_oracle(ext, config, n_frames, iters):
+    st, target, weight = _problem(config, n_frames, 21)
+    lm = torch.tensor([1e-4])
+    t0, t1 = st.t0, st.n
+    rp, rpatch = OB.fastba_forward(st.poses.double(), st.patches.double(), st.intrinsics.double(), target.double(),
+                                   weight.double(), lm.double(), st.ii, st.jj, st.kk, t0, t1, iters)
+    poses = st.poses.clone().to(DEV)[None]
+    patches = st.patches.clone().to(DEV)[None]
+    ext[1].forward(poses, patches, st.intrinsics.to(DEV)[None], target.to(DEV)[None], weight.to(DEV)[None], lm.to(DEV),
+                   st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV), st.cfg["M"], t0, t1, iters, False)
+    torch.cuda.synchronize()
+    dp = (rp - st.poses.double()).abs().max().item()
+    assert dp > 1e-4, "degenerate problem: BA did not move the poses"
+    assert _rel(poses[0].cpu().double()[:t1], rp[:t1]) < 1e-4
+    live = st.kk.unique()
+    assert _rel(patches[0].cpu().double()[live, 2], rpatch[live, 2]) < 1e-4
+    # untouched state stays bit-identical: fixed poses, x/y of patches, patches without edges
+    assert torch.equal(poses[0, :t0].cpu(), st.poses[:t0])
+    assert torch.equal(patches[0, :, :2].cpu(), st.patches[:, :2])
+    # the update is a real correction, not noise: compare step against oracle step
+    assert _rel(poses[0].cpu().double()[t0:t1] - st.poses.double()[t0:t1], rp[t0:t1] - st.poses.double()[t0:t1]) < 2e-3
+
+
+def test_ba_is_deterministic(ext):
+    st, target, weight = _problem("fast", 30, 22)
+    lm = torch.tensor([1e-4], device=DEV)
+    outs = []
+    for _ in range(2):
+        poses = st.poses.clone().to(DEV)[None]
+        patches = st.patches.clone().to(DEV)[None]
+        ext[1].forward(poses, patches, st.intrinsics.to(DEV)[None], target.to(DEV)[None], weight.to(DEV)[None], lm,
+                       st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV), st.cfg["M"], st.t0, st.n, 2, False)
+        outs.append((poses.cpu(), patches.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_ba_structure_only(ext):
+    """t1 - t0 == 0: depth-only branch (ba_cuda.cu:521-531)"""
+    st, target, weight = _problem("fast", 12, 23)
+    lm = torch.tensor([1e-4])
+    rp, rpatch = OB.fastba_forward(st.poses.double(), st.patches.double(), st.intrinsics.double(), target.double(),
+                                   weight.double(), lm.double(), st.ii, st.jj, st.kk, st.n, st.n, 2)
+    poses = st.poses.clone().to(DEV)[None]
+    patches = st.patches.clone().to(DEV)[None]
+    ext[1].forward(poses, patches, st.intrinsics.to(DEV)[None], target.to(DEV)[None], weight.to(DEV)[None], lm.to(DEV),
+                   st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV), st.cfg["M"], st.n, st.n, 2, False)
+    assert torch.equal(poses[0].cpu(), st.poses)
+    live = st.kk.unique()
+    assert _rel(patches[0].cpu().double()[live, 2], rpatch[live, 2]) < 1e-4
+
+
+def test_ba_outliers_and_clamps(ext):
+    """huge residuals are gated (>=128 px), depths are clamped as ba_cuda.cu:218-221"""
+    st, target, weight = _problem("fast", 12, 24, sigma=60.0)
+    st.patches[::7, 2] = 19.9
+    st.patches[3::7, 2] = 2e-4
+    lm = torch.tensor([1e-4])
+    rp, rpatch = OB.fastba_forward(st.poses.double(), st.patches.double(), st.intrinsics.double(), target.double(),
+                                   weight.double(), lm.double(), st.ii, st.jj, st.kk, st.t0, st.n, 2)
+    poses = st.poses.clone().to(DEV)[None]
+    patches = st.patches.clone().to(DEV)[None]
+    ext[1].forward(poses, patches, st.intrinsics.to(DEV)[None], target.to(DEV)[None], weight.to(DEV)[None], lm.to(DEV),
+                   st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV), st.cfg["M"], st.t0, st.n, 2, False)
+    live = st.kk.unique()
+    d = patches[0].cpu().double()[live, 2, 0, 0]
+    r = rpatch[live, 2, 0, 0]
+    # the clamp branches are discontinuous: compare where both sides took the same branch
+    same = ((d == 1.0) == (r == 1.0)) & ((d <= 1e-4) == (r <= 1e-4))
+    assert same.float().mean().item() > 0.98
+    assert ((d[same] - r[same]).abs() <= 1e-3 * r[same].abs() + 1e-6).all()
+    assert _rel(poses[0].cpu().double()[:st.n], rp[:st.n]) < 5e-3
+
+
+def test_reproject_both_modes(ext):
+    st, _, _ = _problem("fast", 20, 25)
+    ii, jj, kk = st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV)
+    out = ext[1].reproject(st.poses.to(DEV)[None], st.patches.to(DEV)[None], st.intrinsics.to(DEV)[None], ii, jj, kk)
+    ref = OB.fastba_reproject(st.poses.double(), st.patches.double(), st.intrinsics.double(), st.ii, st.jj, st.kk)
+    assert out.shape == (1, st.E, 2, 3, 3)
+    assert (out[0].cpu().double() - ref).abs().max().item() < 2e-3       # pixels, fp32 vs fp64
+    out2 = ext[3].reproject_clamped(st.poses.to(DEV)[None], st.patches.to(DEV)[None], st.intrinsics.to(DEV)[None], ii, jj, kk)
+    ref2 = OB.transform(st.poses.double()[None], st.patches.double()[None], st.intrinsics.double()[None], st.ii, st.jj, st.kk)
+    assert (out2[0].cpu().double() - ref2[0].permute(0, 3, 1, 2)).abs().max().item() < 2e-3
+
+
+def test_ba_rejects_what_it_does_not_build(ext):
+    st, target, weight = _problem("fast", 12, 26)
+    poses = st.poses.clone().to(DEV)[None]
+    patches = st.patches.clone().to(DEV)[None]
+    args = (poses, patches, st.intrinsics.to(DEV)[None], target.to(DEV)[None], weight.to(DEV)[None],
+            torch.tensor([1e-4], device=DEV), st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV), st.cfg["M"])
+    with pytest.raises(RuntimeError):
+        ext[1].forward(*args, 1, st.n, 2, True)           # eff_impl (global BA) not built

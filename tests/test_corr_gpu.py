@@ -1,0 +1,135 @@
+"""Parity of cuda_corr (forward, backward, patchify) with the CPU oracle, through the shim -> C-ABI."""
+import pytest
+import torch
+
+from oracle import corr as OC
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _case(seed, M, C=128, S1=40, S2=5, H=30, W=40, dtype=torch.float32, spread=1.0, margin=6.0, cl=False, P=3):
+    g = torch.Generator().manual_seed(seed)
+    f1 = torch.randn(1, S1, C, P, P, generator=g) / 4
+    f2 = torch.randn(1, S2, C, H, W, generator=g) / 4
+    cx = torch.rand(M, generator=g) * (W + 2 * margin) - margin
+    cy = torch.rand(M, generator=g) * (H + 2 * margin) - margin
+    offs = (torch.arange(P).float() - P // 2) * spread
+    coords = torch.zeros(1, M, 2, P, P)
+    coords[0, :, 0] = cx[:, None, None] + offs[None, None, :] + 0.05 * torch.randn(M, P, P, generator=g)
+    coords[0, :, 1] = cy[:, None, None] + offs[None, :, None] + 0.05 * torch.randn(M, P, P, generator=g)
+    ii = torch.randint(0, S1, (M,), generator=g)
+    jj = torch.randint(0, S2, (M,), generator=g)
+    f1, f2 = f1.to(dtype), f2.to(dtype)
+    f1d, f2d = f1.to(DEV), f2.to(DEV)
+    if cl:
+        f1d = f1d.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+        f2d = f2d.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    return f1, f2, coords, ii, jj, f1d, f2d
+
+
+@pytest.mark.parametrize("cl", [False, True])
+@pytest.mark.parametrize("spread", [1.0, 0.25, 2.7])
+def test_corr_forward_fp32(ext, cl, spread):
+    f1, f2, coords, ii, jj, f1d, f2d = _case(1, 300, spread=spread, cl=cl)
+    ref = OC.corr_forward(f1.double(), f2.double(), coords.double(), ii, jj, 3)
+    out, = ext[0].forward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
+    assert out.shape == ref.shape
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= 1e-5 * ref.abs().max().item(), err      # fp32 accumulate vs fp64 oracle
+
+
+def test_corr_forward_fp64(ext):
+    f1, f2, coords, ii, jj, f1d, f2d = _case(2, 100, dtype=torch.float64)
+    ref = OC.corr_forward(f1, f2, coords.double(), ii, jj, 3)
+    out, = ext[0].forward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
+    assert (out.cpu() - ref).abs().max().item() <= 1e-12 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cl", [False, True])
+@pytest.mark.parametrize("spread", [1.0, 0.25, 2.7])
+def test_corr_forward_fp16(ext, cl, spread):
+    """cl=True, C=128 takes the tensor-core kernel; the rest the generic one.  Tolerance: one fp16
+    rounding of the result (2^-11 relative) plus fp32 accumulation noise -- the reference, which
+    accumulates in fp16 (correlation_kernel.cu:121-131), is far outside this bound itself."""
+    f1, f2, coords, ii, jj, f1d, f2d = _case(3, 500, dtype=torch.half, spread=spread, cl=cl)
+    ref = OC.corr_forward(f1.double(), f2.double(), coords.double(), ii, jj, 3)
+    out, = ext[0].forward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
+    err = (out.cpu().double() - ref).abs()
+    tol = 2.0 ** -10 * ref.abs() + 1e-4 * ref.abs().max()
+    assert bool((err <= tol).all()), float((err - tol).max())
+
+
+def test_corr_forward_oob_is_zero(ext):
+    """windows fully outside the map give exact zeros; partially outside match the oracle"""
+    f1, f2, coords, ii, jj, f1d, f2d = _case(4, 64, dtype=torch.half, cl=True)
+    coords[0, :16] += 1000.0
+    coords[0, 16:32] -= 1000.0
+    out, = ext[0].forward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
+    assert float(out[0, :32].abs().max()) == 0.0
+    ref = OC.corr_forward(f1.double(), f2.double(), coords.double(), ii, jj, 3)
+    assert (out.cpu().double() - ref).abs().max().item() <= 2.0 ** -9 * ref.abs().max().item()
+
+
+def test_corr_forward_nonfinite_coords_do_not_crash(ext):
+    f1, f2, coords, ii, jj, f1d, f2d = _case(5, 8, dtype=torch.half, cl=True)
+    coords[0, 0] = float("nan")
+    coords[0, 1] = float("inf")
+    out, = ext[0].forward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out[0, 2:]).all()
+
+
+def test_corr_empty(ext):
+    f1, f2, coords, ii, jj, f1d, f2d = _case(6, 4)
+    out, = ext[0].forward(f1d, f2d, coords[:, :0].to(DEV), ii[:0].to(DEV), jj[:0].to(DEV), 3)
+    assert out.shape == (1, 0, 7, 7, 3, 3)
+
+
+@pytest.mark.parametrize("dtype", [torch.half, torch.float32])
+def test_corr_pyramid2_matches_two_calls(ext, dtype):
+    """fused two-level entry == torch.stack of two single-level calls (dpvo.py:205-207)"""
+    g = torch.Generator().manual_seed(7)
+    S1, S2, H, W, M = 50, 4, 32, 48, 400
+    f1 = (torch.randn(1, S1, 3, 3, 128, generator=g) / 4).to(dtype).to(DEV).permute(0, 1, 4, 2, 3)
+    l0 = (torch.randn(1, S2, H, W, 128, generator=g) / 4).to(dtype).to(DEV).permute(0, 1, 4, 2, 3)
+    l1 = (torch.randn(1, S2, H // 4, W // 4, 128, generator=g) / 4).to(dtype).to(DEV).permute(0, 1, 4, 2, 3)
+    coords = torch.zeros(1, M, 2, 3, 3)
+    offs = torch.arange(3).float() - 1
+    coords[0, :, 0] = (torch.rand(M, generator=g) * (W + 8) - 4)[:, None, None] + offs[None, None, :]
+    coords[0, :, 1] = (torch.rand(M, generator=g) * (H + 8) - 4)[:, None, None] + offs[None, :, None]
+    coords = coords.to(DEV)
+    ii = torch.randint(0, S1, (M,), generator=g).to(DEV)
+    jj = torch.randint(0, S2, (M,), generator=g).to(DEV)
+    a, = ext[0].forward(f1, l0, coords, ii, jj, 3)
+    b, = ext[0].forward(f1, l1, coords / 4, ii, jj, 3)
+    fused = ext[3].corr_pyramid2(f1, l0, l1, coords, ii, jj, 3, 4.0)
+    assert torch.equal(fused, torch.stack([a, b], -1))
+
+
+@pytest.mark.parametrize("cl", [False, True])
+def test_corr_backward_fp32(ext, cl):
+    f1, f2, coords, ii, jj, f1d, f2d = _case(8, 60, C=128, S1=20, S2=3, H=20, W=24, cl=cl)
+    g = torch.Generator().manual_seed(9)
+    grad = torch.randn(1, 60, 7, 7, 3, 3, generator=g)
+    a = f1.double().requires_grad_(True)
+    b = f2.double().requires_grad_(True)
+    OC.corr_forward(a, b, coords.double(), ii, jj, 3).backward(grad.double())
+    g1, g2 = ext[0].backward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), grad.to(DEV), 3)
+    assert (g1.cpu().double() - a.grad).abs().max().item() <= 2e-5 * a.grad.abs().max().item()
+    assert (g2.cpu().double() - b.grad).abs().max().item() <= 2e-5 * b.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("radius,C", [(0, 384), (1, 128), (0, 1), (1, 3)])
+def test_patchify_forward_backward(ext, radius, C):
+    g = torch.Generator().manual_seed(10 + radius)
+    net = torch.randn(2, C, 30, 40, generator=g)
+    coords = torch.stack([torch.rand(2, 96, generator=g) * 44 - 2, torch.rand(2, 96, generator=g) * 34 - 2], -1)
+    ref = OC.patchify_raw(net, coords, radius)
+    out, = ext[0].patchify_forward(net.to(DEV), coords.to(DEV), radius)
+    assert torch.equal(out.cpu(), ref)          # pure gather: bit exact
+    grad = torch.randn(ref.shape, generator=g)
+    n = net.clone().requires_grad_(True)
+    OC.patchify_raw(n, coords, radius).backward(grad)
+    gout, = ext[0].patchify_backward(net.to(DEV), coords.to(DEV), grad.to(DEV), radius)
+    assert (gout.cpu() - n.grad).abs().max().item() <= 1e-5
