@@ -270,7 +270,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="default", choices=["default", "fast"])
-    ap.add_argument("--gemm", default="cublas", choices=["cublas", "tcgen05"])
+    ap.add_argument("--gemm", default="tcgen05", choices=["cublas", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

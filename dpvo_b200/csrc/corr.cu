@@ -38,6 +38,7 @@ struct CorrArgs {
   const int64_t* jj;
   void* out;
   int64_t out_stride;   // element stride between consecutive logical outputs
+  int64_t out_row;      // element stride between consecutive (b, m) rows
   int out_offset[2];    // element offset of each level inside one logical output slot
   int nlev;             // 1 or 2 levels handled by this launch
   int B, M, C, P, R;
@@ -198,7 +199,7 @@ corr_fwd_generic(const CorrArgs a, int Cpad) {
 
       // ---- bilinear blend (correlation_kernel.cu:221-230) + (x,y) offset order (:232)
       const int nout = O * O * PP;
-      T* o = out + ((int64_t)(b * a.M + m) * nout) * a.out_stride + a.out_offset[lev];
+      T* o = out + (int64_t)(b * a.M + m) * a.out_row + a.out_offset[lev];
       for (int q = tid; q < nout; q += GEN_THREADS) {
         const int p = q % PP, t = q / PP, yo = t % O, xo = t / O;
         const A dx = (A)meta_f[p], dy = (A)meta_f[PP + p];
@@ -383,9 +384,9 @@ corr_fwd_mma(const CorrArgs a) {
                           (1.f - dx) * dy * rp[D] + dx * dy * rp[D + 1];
           if constexpr (PAIR_OUT) {
             if (lev == 0) keep[i] = v;
-            else reinterpret_cast<__half2*>(out)[(int64_t)(b * a.M + m) * NOUT + q] = __floats2half2_rn(keep[i], v);
+            else reinterpret_cast<__half2*>(out + (int64_t)(b * a.M + m) * a.out_row)[q] = __floats2half2_rn(keep[i], v);
           } else {
-            out[((int64_t)(b * a.M + m) * NOUT + q) * a.out_stride + a.out_offset[lev]] = __float2half_rn(v);
+            out[(int64_t)(b * a.M + m) * a.out_row + (int64_t)q * a.out_stride + a.out_offset[lev]] = __float2half_rn(v);
           }
         }
       }
@@ -687,6 +688,7 @@ extern "C" int dpvo_corr_forward(const void* fmap1, const int64_t* fmap1_strides
   a.H2[0] = H2; a.W2[0] = W2; a.div[0] = 1.0f;
   a.coords = coords; a.ii = ii; a.jj = jj; a.out = out; a.out_stride = out_elem_stride;
   a.out_offset[0] = 0; a.nlev = 1; a.B = B; a.M = M; a.C = C; a.P = P; a.R = radius;
+  a.out_row = (int64_t)(2 * radius + 1) * (2 * radius + 1) * P * P * out_elem_stride;
   return corr_dispatch(a, dtype, false, (cudaStream_t)stream);
 }
 
@@ -695,12 +697,14 @@ extern "C" int dpvo_corr_forward_pyramid2(const void* fmap1, const int64_t* fmap
                                           const void* fmap2_l1, const int64_t* l1_strides, int H1, int W1,
                                           float lvl1_div,
                                           const float* coords, const int64_t* ii, const int64_t* jj,
-                                          void* out,
+                                          void* out, int64_t out_row_stride,
                                           int dtype, int B, int M, int C, int P,
                                           int S1, int S2, int radius, void* stream) {
   DPVO_REQUIRE(B >= 0 && M >= 0 && C > 0 && P > 0 && radius >= 0 && H0 > 0 && W0 > 0 && H1 > 0 && W1 > 0,
                "corr_forward_pyramid2: bad sizes");
   DPVO_REQUIRE(lvl1_div > 0.f, "corr_forward_pyramid2: lvl1_div must be > 0");
+  DPVO_REQUIRE(out_row_stride >= 2 * (int64_t)(2 * radius + 1) * (2 * radius + 1) * P * P && out_row_stride % 2 == 0,
+               "corr_forward_pyramid2: bad out_row_stride");
   if ((int64_t)B * M == 0) return DPVO_OK;
   DPVO_REQUIRE(fmap1 && fmap2_l0 && fmap2_l1 && coords && ii && jj && out && fmap1_strides && l0_strides && l1_strides,
                "corr_forward_pyramid2: null pointer");
@@ -712,6 +716,7 @@ extern "C" int dpvo_corr_forward_pyramid2(const void* fmap1, const int64_t* fmap
   a.H2[0] = H0; a.W2[0] = W0; a.H2[1] = H1; a.W2[1] = W1; a.div[0] = 1.0f; a.div[1] = lvl1_div;
   a.coords = coords; a.ii = ii; a.jj = jj; a.out = out; a.out_stride = 2;
   a.out_offset[0] = 0; a.out_offset[1] = 1; a.nlev = 2; a.B = B; a.M = M; a.C = C; a.P = P; a.R = radius;
+  a.out_row = out_row_stride;
   return corr_dispatch(a, dtype, true, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,320 @@
+// Dense layers of the update operator on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+//   Y[rows, N] = epilogue( X[rows, K] @ W[N, K]^T + bias )        fp16 operands, fp32 accumulate
+//
+// Persistent, warp-specialised kernel (one CTA per SM):
+//   warps 0-3  epilogue     tcgen05.ld the 128 x 192 fp32 accumulator tile out of TMEM (each warp owns
+//                           its 32-lane quarter), bias / activation / residual, fp16 or fp32 store
+//   warp  4    MMA issuer   one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//                           (M=128, N=192, K=16) on shared-memory descriptors, accumulators in TMEM,
+//                           double buffered (2 x 192 of the 512 columns) so the epilogue of tile i
+//                           overlaps the main loop of tile i+1; tcgen05.commit releases smem stages and
+//                           publishes finished accumulators through mbarriers
+//   warps 5-8  producers    stage X and W k-blocks (64 halves = one 128-byte swizzle atom per row) into a
+//                           5-deep shared-memory ring with 16-byte cp.async in the SWIZZLE_128B K-major
+//                           layout the UMMA descriptors expect; X rows may be gathered through an index
+//                           (net.py:84-85 `net[:, ix]` with mask) so the gather never touches HBM twice
+// The weights (<= 0.7 MB per layer) stay L2 resident; X is read once per 192-column half.
+#include "common.cuh"
+
+namespace dpvo {
+
+constexpr int GM_M = 128;            // rows per tile == TMEM lanes
+constexpr int GM_N = 192;            // columns per tile (UMMA N, multiple of 16)
+constexpr int GM_K = 64;             // halves per k-block: 128 bytes, one swizzle atom
+constexpr int GM_UK = 16;            // UMMA K for 16-bit operands
+constexpr int GM_STAGES = 5;
+constexpr int GM_LOOK = 2;           // cp.async groups kept in flight per producer thread
+constexpr int GM_EPI_THREADS = 128, GM_PROD_THREADS = 128;
+constexpr int GM_THREADS = GM_EPI_THREADS + 32 + GM_PROD_THREADS;
+constexpr int GM_A_BYTES = GM_M * 128, GM_B_BYTES = GM_N * 128;
+constexpr int GM_TMEM_COLS = 512;
+
+struct GemmArgs {
+  const __half* X; int64_t ldx;
+  const __half* W; int64_t ldw;
+  const float* bias;
+  const int64_t* gather;       // optional row indirection for X (-1 -> zero row)
+  const void* res; int res_dtype; int64_t ldres;
+  const __half* gate; int64_t ldgate;
+  void* Y; int y_dtype; int64_t ldy;
+  __half* Y16;                 // optional fp16 copy of the result (row stride ldy16)
+  int64_t ldy16;
+  int64_t rows; int N; int K; int epilogue;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor):
+// start address >> 4 | LBO (unused for swizzled K-major, canonical value 1) | SBO = 8 rows * 128 B |
+// version 1 (Blackwell) | layout type 2 (SWIZZLE_128B).  The tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (InstrDescriptor): D fp32, A/B fp16 K-major, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t GM_IDESC = (1u << 4) | ((uint32_t)(GM_N >> 3) << 17) | ((uint32_t)(GM_M >> 4) << 24);
+
+struct GemmBars {
+  uint64_t full[GM_STAGES], empty[GM_STAGES], tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float epi_act(float v, int epi) {
+  if (epi == DPVO_EPI_RELU) return fmaxf(v, 0.f);
+  if (epi == DPVO_EPI_SIGMOID) return 1.0f / (1.0f + __expf(-v));
+  return v;
+}
+
+__global__ void __launch_bounds__(GM_THREADS, 1)
+linear_f16_kernel(const GemmArgs a) {
+  extern __shared__ unsigned char gm_smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)gm_smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = base;
+  unsigned char* sB = base + GM_STAGES * GM_A_BYTES;
+  GemmBars* bars = reinterpret_cast<GemmBars*>(base + GM_STAGES * (GM_A_BYTES + GM_B_BYTES));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles_n = (a.N + GM_N - 1) / GM_N;
+  const int64_t n_tiles_m = (a.rows + GM_M - 1) / GM_M;
+  const int64_t n_tiles = n_tiles_m * n_tiles_n;
+  const int KB = a.K / GM_K;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GM_STAGES; ++s) { mbar_init(&bars->full[s], GM_PROD_THREADS); mbar_init(&bars->empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], GM_EPI_THREADS); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&bars->tmem_base)), "n"(GM_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp >= 5) {
+    // =========================================================================== producers
+    const int pt = threadIdx.x - (GM_EPI_THREADS + 32);
+    uint32_t it = 0;                       // k-block counter over all tiles of this CTA
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t m0 = (tile / n_tiles_n) * GM_M;
+      const int n0 = (int)(tile % n_tiles_n) * GM_N;
+      // per-thread row pointers of the 8 A chunks and 12 B chunks it copies per k-block
+      const __half* arow[8]; uint32_t aoff[8], abytes[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = pt + GM_PROD_THREADS * i, row = c >> 3, ch = c & 7;
+        int64_t src = m0 + row;
+        bool ok = src < a.rows;
+        if (ok && a.gather) { src = a.gather[src]; ok = src >= 0; }
+        arow[i] = a.X + (ok ? src : 0) * a.ldx + ch * 8;
+        abytes[i] = ok ? 16u : 0u;
+        aoff[i] = row * 128 + ((ch ^ (row & 7)) << 4);
+      }
+      const __half* brow[12]; uint32_t boff[12], bbytes[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const int c = pt + GM_PROD_THREADS * i, row = c >> 3, ch = c & 7;
+        const bool ok = n0 + row < a.N;
+        brow[i] = a.W + (int64_t)(ok ? n0 + row : 0) * a.ldw + ch * 8;
+        bbytes[i] = ok ? 16u : 0u;
+        boff[i] = row * 128 + ((ch ^ (row & 7)) << 4);
+      }
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const uint32_t s = it % GM_STAGES, ph = (it / GM_STAGES) & 1;
+        mbar_wait(&bars->empty[s], ph ^ 1);
+        const uint32_t da = smem_u32(sA + s * GM_A_BYTES), db = smem_u32(sB + s * GM_B_BYTES);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async16(da + aoff[i], arow[i] + kb * GM_K, abytes[i]);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) cp_async16(db + boff[i], brow[i] + kb * GM_K, bbytes[i]);
+        cp_async_commit();
+        if (it >= GM_LOOK) {               // the group issued GM_LOOK k-blocks ago has landed
+          cp_async_wait<GM_LOOK>();
+          fence_proxy_async();
+          mbar_arrive(&bars->full[(it - GM_LOOK) % GM_STAGES]);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (uint32_t j = (it >= GM_LOOK ? it - GM_LOOK : 0); j < it; ++j) mbar_arrive(&bars->full[j % GM_STAGES]);
+  } else if (warp == 4) {
+    // =========================================================================== MMA issuer
+    uint32_t it = 0, tcount = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(&bars->tmem_empty[acc], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * GM_N;
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const uint32_t s = it % GM_STAGES, ph = (it / GM_STAGES) & 1;
+        mbar_wait(&bars->full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * GM_A_BYTES));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sB + s * GM_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GM_K / GM_UK; ++k)
+            tc_mma_f16(d_tmem, ad + (uint64_t)(k * GM_UK * 2 / 16), bd + (uint64_t)(k * GM_UK * 2 / 16), GM_IDESC, (kb | k) != 0);
+          tc_commit(&bars->empty[s]);                      // smem stage reusable once these MMAs retire
+          if (kb == KB - 1) tc_commit(&bars->tmem_full[acc]);   // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================================================================== epilogue
+    uint32_t tcount = 0;
+    const int row_in_tile = warp * 32 + lane;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      const int64_t row = (tile / n_tiles_n) * GM_M + row_in_tile;
+      const int n0 = (int)(tile % n_tiles_n) * GM_N;
+      mbar_wait(&bars->tmem_full[acc], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * GM_N;
+      const bool row_ok = row < a.rows;
+#pragma unroll 1
+      for (int c0 = 0; c0 < GM_N; c0 += 16) {
+        uint32_t r[16];
+        tc_ld16(taddr + c0, r);
+        tc_ld_wait();
+        const int col = n0 + c0;
+        if (row_ok && col < a.N) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (a.bias ? a.bias[col + j] : 0.f);
+          if (a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float g = 1.f;
+              if (a.epilogue == DPVO_EPI_GATEDRES) g = __half2float(a.gate[row * a.ldgate + col + j]);
+              const float rv = (a.res_dtype == DPVO_F32) ? reinterpret_cast<const float*>(a.res)[row * a.ldres + col + j]
+                                                         : __half2float(reinterpret_cast<const __half*>(a.res)[row * a.ldres + col + j]);
+              v[j] = rv + g * v[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = epi_act(v[j], a.epilogue);
+          }
+          if (a.y_dtype == DPVO_F16) {
+            uint4 o[2];
+            __half2* h = reinterpret_cast<__half2*>(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.Y) + row * a.ldy + col);
+            dst[0] = o[0]; dst[1] = o[1];
+          } else {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + row * a.ldy + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (a.Y16) {
+            uint4 o[2];
+            __half2* h = reinterpret_cast<__half2*>(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            uint4* dst = reinterpret_cast<uint4*>(a.Y16 + row * a.ldy16 + col);
+            dst[0] = o[0]; dst[1] = o[1];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(GM_TMEM_COLS));
+  }
+}
+
+}  // namespace dpvo
+
+using namespace dpvo;
+
+static int linear_launch(const GemmArgs& a, cudaStream_t st) {
+  const size_t smem = GM_STAGES * (GM_A_BYTES + GM_B_BYTES) + sizeof(GemmBars) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(linear_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "linear_f16: cudaFuncSetAttribute");
+    attr = true;
+  }
+  const int64_t tiles = ((a.rows + GM_M - 1) / GM_M) * ((a.N + GM_N - 1) / GM_N);
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
+  linear_f16_kernel<<<grid, GM_THREADS, smem, st>>>(a);
+  DPVO_LAUNCH_CHECK("linear_f16_kernel");
+  return DPVO_OK;
+}
+
+extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather, const void* W, int64_t ldw,
+                               const float* bias, const void* res, int res_dtype, int64_t ldres,
+                               const void* gate, int64_t ldgate, void* Y, int y_dtype, int64_t ldy,
+                               void* Y16, int64_t ldy16,
+                               int64_t rows, int N, int K, int epilogue, void* stream) {
+  DPVO_REQUIRE(rows >= 0 && N > 0 && K > 0, "linear_f16: bad sizes");
+  if (rows == 0) return DPVO_OK;
+  DPVO_REQUIRE(X && W && Y, "linear_f16: null pointer");
+  DPVO_REQUIRE(K % GM_K == 0, "linear_f16: K=%d must be a multiple of %d (pad the operands)", K, GM_K);
+  DPVO_REQUIRE(N % 16 == 0, "linear_f16: N=%d must be a multiple of 16", N);
+  DPVO_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)W & 15) == 0,
+               "linear_f16: X / W rows must be 16-byte aligned");
+  DPVO_REQUIRE(y_dtype == DPVO_F16 || y_dtype == DPVO_F32, "linear_f16: y dtype");
+  DPVO_REQUIRE((y_dtype == DPVO_F16 ? ldy % 8 == 0 : ldy % 4 == 0) && ((uintptr_t)Y & 15) == 0, "linear_f16: Y rows must be 16-byte aligned");
+  DPVO_REQUIRE(epilogue >= DPVO_EPI_NONE && epilogue <= DPVO_EPI_GATEDRES, "linear_f16: unknown epilogue %d", epilogue);
+  if (epilogue == DPVO_EPI_RESADD || epilogue == DPVO_EPI_GATEDRES)
+    DPVO_REQUIRE(res && (res_dtype == DPVO_F16 || res_dtype == DPVO_F32), "linear_f16: residual operand missing");
+  if (epilogue == DPVO_EPI_GATEDRES) DPVO_REQUIRE(gate, "linear_f16: gate operand missing");
+  GemmArgs a;
+  a.X = (const __half*)X; a.ldx = ldx; a.W = (const __half*)W; a.ldw = ldw; a.bias = bias; a.gather = gather;
+  a.res = res; a.res_dtype = res_dtype; a.ldres = ldres; a.gate = (const __half*)gate; a.ldgate = ldgate;
+  DPVO_REQUIRE(!Y16 || (ldy16 % 8 == 0 && ((uintptr_t)Y16 & 15) == 0), "linear_f16: Y16 rows must be 16-byte aligned");
+  a.Y16 = (__half*)Y16; a.ldy16 = ldy16;
+  a.Y = Y; a.y_dtype = y_dtype; a.ldy = ldy; a.rows = rows; a.N = N; a.K = K; a.epilogue = epilogue;
+  return linear_launch(a, (cudaStream_t)stream);
+}

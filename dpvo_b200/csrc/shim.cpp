@@ -265,17 +265,20 @@ Tensor l_jinv(int g, Tensor X, Tensor a) { return lie_binary(dpvo_lie_jinv, g, X
 
 // ------------------------------------------------------------------------- dpvo_b200_ext
 // DPVO.corr (dpvo.py:200-207) in one launch: returns [1, E, 882]-compatible [B,M,O,O,P,P,2]
-Tensor corr_pyramid2(Tensor fmap1, Tensor fmap2_l0, Tensor fmap2_l1, Tensor coords, Tensor ii, Tensor jj, int radius, double div) {
+Tensor corr_pyramid2(Tensor fmap1, Tensor fmap2_l0, Tensor fmap2_l1, Tensor coords, Tensor ii, Tensor jj, int radius, double div, int64_t pad_to) {
   need_cuda(fmap1, "fmap1");
   c10::cuda::CUDAGuard guard(fmap1.device());
   coords = f32c(coords); ii = i64c(ii); jj = i64c(jj);
   const int B = coords.size(0), M = coords.size(1), P = coords.size(3), C = fmap1.size(2), O = 2 * radius + 1;
-  Tensor out = torch::empty({B, M, O, O, P, P, 2}, fmap1.options());
+  const int64_t feat = (int64_t)O * O * P * P * 2;
+  const int64_t row = pad_to > feat ? pad_to : feat;
+  // padded rows ([B, M, row], zero tail) feed the tcgen05 dense layer directly; unpadded keep the 7-d view
+  Tensor out = (row == feat) ? torch::empty({B, M, O, O, P, P, 2}, fmap1.options()) : torch::zeros({B, M, row}, fmap1.options());
   auto s1 = strides5(fmap1), s20 = strides5(fmap2_l0), s21 = strides5(fmap2_l1);
   check(dpvo_corr_forward_pyramid2(fmap1.data_ptr(), s1.data(), fmap2_l0.data_ptr(), s20.data(), (int)fmap2_l0.size(3),
                                    (int)fmap2_l0.size(4), fmap2_l1.data_ptr(), s21.data(), (int)fmap2_l1.size(3),
                                    (int)fmap2_l1.size(4), (float)div, coords.data_ptr<float>(), ii.data_ptr<int64_t>(),
-                                   jj.data_ptr<int64_t>(), out.data_ptr(), dt(fmap1), B, M, C, P, (int)fmap1.size(1),
+                                   jj.data_ptr<int64_t>(), out.data_ptr(), row, dt(fmap1), B, M, C, P, (int)fmap1.size(1),
                                    (int)fmap2_l0.size(1), radius, stream()),
         "dpvo_b200_ext.corr_pyramid2");
   return out;
@@ -395,6 +398,37 @@ Tensor softagg_reduce(Tensor fg, Tensor order, Tensor group_start, Tensor n_grou
   return y;
 }
 
+// Y = epilogue(X @ W^T + bias) on tcgen05; X [.., rows, K] fp16 (row stride may exceed K), W [N, K] fp16
+Tensor linear_f16(Tensor x, Tensor w, c10::optional<Tensor> bias, int64_t epilogue, c10::optional<Tensor> res,
+                  c10::optional<Tensor> gate, c10::optional<Tensor> gather, bool out_f32, c10::optional<Tensor> out,
+                  c10::optional<Tensor> out16) {
+  need_cuda(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.scalar_type() == at::kHalf && w.scalar_type() == at::kHalf, "linear_f16: fp16 operands expected");
+  TORCH_CHECK(x.stride(-1) == 1 && w.dim() == 2 && w.stride(1) == 1, "linear_f16: K must be contiguous");
+  const int K = w.size(1), N = w.size(0);
+  TORCH_CHECK(x.size(-1) == K, "linear_f16: X has ", x.size(-1), " columns, W expects ", K);
+  Tensor x2 = x.dim() == 2 ? x : x.reshape({-1, K});
+  TORCH_CHECK(x2.stride(1) == 1, "linear_f16: X rows must be dense");
+  Tensor gi, b, r, g;
+  int64_t rows = x2.size(0);
+  if (gather.has_value()) { gi = i64c(*gather); rows = gi.numel(); }
+  if (bias.has_value()) b = f32c(*bias);
+  int res_dt = DPVO_F32; int64_t ldres = 0, ldgate = 0;
+  if (res.has_value()) { r = res->reshape({-1, N}); TORCH_CHECK(r.stride(1) == 1 && r.size(0) == rows, "linear_f16: res shape"); res_dt = dt16or32(r); ldres = r.stride(0); }
+  if (gate.has_value()) { g = gate->reshape({-1, N}); TORCH_CHECK(g.scalar_type() == at::kHalf && g.stride(1) == 1 && g.size(0) == rows, "linear_f16: gate shape"); ldgate = g.stride(0); }
+  Tensor y = out.has_value() ? *out : torch::empty({1, rows, N}, x.options().dtype(out_f32 ? at::kFloat : at::kHalf));
+  TORCH_CHECK(y.is_contiguous() && y.numel() == rows * N && y.scalar_type() == (out_f32 ? at::kFloat : at::kHalf), "linear_f16: out tensor");
+  Tensor y16;
+  if (out16.has_value()) { y16 = *out16; TORCH_CHECK(y16.is_contiguous() && y16.numel() == rows * N && y16.scalar_type() == at::kHalf, "linear_f16: out16 tensor"); }
+  check(dpvo_linear_f16(x2.data_ptr(), x2.stride(0), gi.defined() ? gi.data_ptr<int64_t>() : nullptr, w.data_ptr(), w.stride(0),
+                        b.defined() ? b.data_ptr<float>() : nullptr, r.defined() ? r.data_ptr() : nullptr, res_dt, ldres,
+                        g.defined() ? g.data_ptr() : nullptr, ldgate, y.data_ptr(), out_f32 ? DPVO_F32 : DPVO_F16, N,
+                        y16.defined() ? y16.data_ptr() : nullptr, N, rows, N, K, (int)epilogue, stream()),
+        "dpvo_b200_ext.linear_f16");
+  return y;
+}
+
 std::vector<Tensor> neighbors_from_groups(Tensor order, Tensor group_of) {
   need_cuda(order, "order");
   c10::cuda::CUDAGuard guard(order.device());
@@ -464,7 +498,8 @@ PYBIND11_MODULE(lietorch_backends, m) {
 }
 
 PYBIND11_MODULE(dpvo_b200_ext, m) {
-  m.def("corr_pyramid2", &corr_pyramid2, "two-level fused correlation");
+  m.def("corr_pyramid2", &corr_pyramid2, "two-level fused correlation", py::arg("fmap1"), py::arg("fmap2_l0"), py::arg("fmap2_l1"),
+        py::arg("coords"), py::arg("ii"), py::arg("jj"), py::arg("radius"), py::arg("div"), py::arg("pad_to") = 0);
   m.def("group_edges", &group_edges, "device edge grouping", py::arg("key_a"), py::arg("key_b") = py::none(),
         py::arg("sec") = py::none());
   m.def("reproject_clamped", &reproject_clamped, "pops.transform-compatible fused reprojection");
@@ -474,6 +509,9 @@ PYBIND11_MODULE(dpvo_b200_ext, m) {
   m.def("gated_residual", &gated_residual, "x + sigmoid(g) * r");
   m.def("softagg_reduce", &softagg_reduce, "segment softmax-weighted sum");
   m.def("update_heads", &update_heads, "delta / weight heads");
+  m.def("linear_f16", &linear_f16, "tcgen05 dense layer", py::arg("x"), py::arg("w"), py::arg("bias") = py::none(),
+        py::arg("epilogue") = 0, py::arg("res") = py::none(), py::arg("gate") = py::none(), py::arg("gather") = py::none(),
+        py::arg("out_f32") = false, py::arg("out") = py::none(), py::arg("out16") = py::none());
   m.def("neighbors_from_groups", &neighbors_from_groups, "temporal neighbours from a kk/jj grouping");
   m.def("launch_count", &launch_count, "kernel launches issued by libdpvo_b200 so far");
   m.def("version", &version, "library version string");

@@ -20,6 +20,7 @@ import torch.nn.functional as F
 from . import extensions
 
 DIM = 384
+CORR_PAD = 896      # 2*49*9 = 882 correlation features rounded up to a multiple of 64
 
 
 class GradClip(torch.autograd.Function):
@@ -93,6 +94,10 @@ class Update(nn.Module):
             return (m.weight.detach().half().contiguous(), m.bias.detach().float().contiguous())
         P = {}
         P["corr0"], P["corr2"], P["corr5"] = lin(self.corr[0]), lin(self.corr[2]), lin(self.corr[5])
+        # the first dense layer consumes correlation rows padded from 882 to 896 columns (one 64-wide
+        # k-block of the tcgen05 kernel); the extra weight columns are zero
+        w0, b0 = P["corr0"]
+        P["corr0"] = (F.pad(w0, (0, CORR_PAD - w0.shape[1])).contiguous(), b0)
         P["c1a"], P["c1b"], P["c2a"], P["c2b"] = lin(self.c1[0]), lin(self.c1[2]), lin(self.c2[0]), lin(self.c2[2])
         for nm, agg in (("kk", self.agg_kk), ("ij", self.agg_ij)):
             # f and g share their input: one GEMM with N = 768
@@ -107,49 +112,80 @@ class Update(nn.Module):
         return P
 
     def dense(self, x16, wb, relu=False):
+        """library baseline: cuBLAS through torch"""
         w, b = wb
-        if self.gemm == "cublas":
-            y = F.linear(x16, w, b.half())
-            return F.relu_(y) if relu else y
-        raise RuntimeError("Update: unknown gemm backend %r" % self.gemm)
+        y = F.linear(x16, w, b.half())
+        return F.relu_(y) if relu else y
 
     # ------------------------------------------------------------------------------- forward
     @torch.no_grad()
     def forward(self, net, inp, corr, flow, ii, jj, kk, groups_kk=None, groups_ij=None):
-        """net [1,E,384] (fp16 or fp32), inp [1,E,384], corr [1,E,882], ii/jj/kk int64 [E].
+        """net [1,E,384] (fp16 or fp32), inp [1,E,384], corr [1,E,882 or 896], ii/jj/kk int64 [E].
         Returns (net fp32, (delta [1,E,2], weight [1,E,2], None)) like net.py:92."""
+        corr = corr if corr.dtype == torch.half else corr.half()
+        if corr.shape[-1] != CORR_PAD:
+            corr = F.pad(corr, (0, CORR_PAD - corr.shape[-1]))
+        inp = inp if inp.dtype in (torch.half, torch.float32) else inp.half()
+        if groups_kk is None:
+            groups_kk = EdgeGroups(kk, None, jj)
+        if groups_ij is None:
+            groups_ij = EdgeGroups(ii, jj, None)
+        if self.gemm == "tcgen05":
+            return self._forward_tcgen05(net, inp, corr, groups_kk, groups_ij)
+        if self.gemm == "cublas":
+            return self._forward_cublas(net, inp, corr, groups_kk, groups_ij)
+        raise RuntimeError("Update: unknown gemm backend %r" % self.gemm)
+
+    def _forward_tcgen05(self, net, inp, corr, groups_kk, groups_ij):
+        """every dense layer on dpvo_linear_f16, with the gather / residual / gating fused into the
+        operand load and the epilogue"""
         ex = extensions()[3]
         P = self._packed or self.pack()
-        E = net.shape[1]
-        corr = corr.half() if corr.dtype != torch.half else corr
-        inp = inp.half() if inp.dtype not in (torch.half, torch.float32) else inp
+        NONE, RELU, SIGM, RESADD, GATED = 0, 1, 2, 3, 4
 
-        # corr MLP (net.py:53-60) and the first LayerNorm (:77-78)
+        def L(x, name, epi=NONE, **kw):
+            wgt, b = P[name]
+            return ex.linear_f16(x, wgt, b, epi, **kw)
+
+        h = L(L(corr, "corr0", RELU), "corr2")
+        _, h = ex.add_layernorm(h, None, None, self.corr[3].weight, self.corr[3].bias, 1e-3, True, False, True)
+        h = L(h, "corr5")
+        net32, n16 = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, True)
+        ix, jx = ex.neighbors_from_groups(groups_kk.order, groups_kk.group_of)
+        for idx, a, b in ((ix, "c1a", "c1b"), (jx, "c2a", "c2b")):
+            u = L(n16, a, RELU, gather=idx)                       # c(mask * net[idx]) first layer
+            n16 = torch.empty_like(n16)
+            L(u, b, RESADD, res=net32, out_f32=True, out=net32, out16=n16)   # net += second layer
+        for grp, nm in ((groups_kk, "kk"), (groups_ij, "ij")):
+            y = ex.softagg_reduce(L(n16, "fg_" + nm), grp.order, grp.group_start, grp.n, grp.max_groups)
+            n16 = ex.residual_add_(net32, L(y, "h_" + nm), grp.group_of, True)
+        x32 = net32
+        for i, ln in ((1, self.gru[0]), (3, self.gru[2])):
+            x32, x16 = ex.add_layernorm(x32, None, None, ln.weight, ln.bias, 1e-3, False, True, True)
+            gate = L(x16, "gr%d_g" % i, SIGM)
+            r1 = L(x16, "gr%d_a" % i, RELU)
+            L(r1, "gr%d_b" % i, GATED, res=x32, gate=gate, out_f32=True, out=x32)
+        delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"])
+        return x32, (delta, weight, None)
+
+    def _forward_cublas(self, net, inp, corr, groups_kk, groups_ij):
+        ex = extensions()[3]
+        P = self._packed or self.pack()
         h = self.dense(corr, P["corr0"], relu=True)
         h = self.dense(h, P["corr2"])
         _, h = ex.add_layernorm(h, None, None, self.corr[3].weight, self.corr[3].bias, 1e-3, True, False, True)
         h = self.dense(h, P["corr5"])
         net32, _ = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, False)
-
-        # temporal neighbours of every edge along its patch track (net.py:80-85)
-        if groups_kk is None:
-            groups_kk = EdgeGroups(kk, None, jj)
         ix, jx = ex.neighbors_from_groups(groups_kk.order, groups_kk.group_of)
+        n16 = None
         for idx, a, b in ((ix, "c1a", "c1b"), (jx, "c2a", "c2b")):
             g16 = ex.gather_rows_masked(net32, idx, True)
             u = self.dense(self.dense(g16, P[a], relu=True), P[b])
             n16 = ex.residual_add_(net32, u, None, idx is jx)
-
-        # soft aggregation over patches, then over frame pairs (net.py:87-88, blocks.py:40-48)
-        if groups_ij is None:
-            groups_ij = EdgeGroups(ii, jj, None)
         for grp, nm in ((groups_kk, "kk"), (groups_ij, "ij")):
             fg = self.dense(n16, P["fg_" + nm])
             y = ex.softagg_reduce(fg, grp.order, grp.group_start, grp.n, grp.max_groups)
-            hy = self.dense(y, P["h_" + nm])
-            n16 = ex.residual_add_(net32, hy, grp.group_of, True)
-
-        # 2 x (LayerNorm, gated residual) (net.py:46-51, blocks.py:28-29)
+            n16 = ex.residual_add_(net32, self.dense(y, P["h_" + nm]), grp.group_of, True)
         x32 = net32
         for i, ln in ((1, self.gru[0]), (3, self.gru[2])):
             x32, x16 = ex.add_layernorm(x32, None, None, ln.weight, ln.bias, 1e-3, False, True, True)

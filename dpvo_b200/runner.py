@@ -56,7 +56,7 @@ class UpdateRunner:
         coords = pops.transform_fused(poses, patches, intr, s.ii, s.jj, s.kk)               # [1,E,2,3,3]
         if ev is not None:
             ev["corr0"].record()
-        corr = altcorr.corr_pyramid(s.gmap, (s.fmap1, s.fmap2), coords, self.kk_ring, self.jj_ring, 3, 4.0)
+        corr = altcorr.corr_pyramid(s.gmap, (s.fmap1, s.fmap2), coords, self.kk_ring, self.jj_ring, 3, 4.0, 896)
         if ev is not None:
             ev["corr1"].record()
         ctx = s.imap[:, self.kk_ring]

@@ -83,15 +83,16 @@ int dpvo_corr_forward(const void* fmap1, const int64_t* fmap1_strides,
 /*
  * Two-level fused form of DPVO.corr (dpvo/dpvo.py:200-207): level 0 samples fmap2_l0 at coords,
  * level 1 samples fmap2_l1 at coords / lvl1_div (4 in DPVO), result written as
- * out[B, M, 2R+1, 2R+1, P, P, 2] (level innermost) == torch.stack([c0, c1], -1).
- * B must be 1 batch stride aware through strides as above.
+ * out[B, M, 2R+1, 2R+1, P, P, 2] (level innermost) == torch.stack([c0, c1], -1).  Consecutive
+ * (b, m) rows are out_row_stride elements apart (>= 2*(2R+1)^2*P^2, even; 896 pads the 882 features of
+ * DPVO to the k-block of the first dense layer -- padding columns are not written).
  */
 int dpvo_corr_forward_pyramid2(const void* fmap1, const int64_t* fmap1_strides,
                                const void* fmap2_l0, const int64_t* l0_strides, int H0, int W0,
                                const void* fmap2_l1, const int64_t* l1_strides, int H1, int W1,
                                float lvl1_div,
                                const float* coords, const int64_t* ii, const int64_t* jj,
-                               void* out,
+                               void* out, int64_t out_row_stride,
                                int dtype, int B, int M, int C, int P,
                                int S1, int S2, int radius, void* stream);
 
@@ -298,25 +299,30 @@ int dpvo_update_heads(const void* net32, const float* W4, const float* b4, float
                       int64_t rows, int dim, void* stream);
 
 /*
- * Dense layer on tensor cores (tcgen05, fp16 operands, fp32 accumulate in TMEM):
+ * Dense layer on tensor cores (tcgen05.mma, fp16 operands, fp32 accumulation in TMEM):
  *   Y = epilogue( X[rows, K] @ W[N, K]^T + bias[N] )
- * X, W fp16 row-major (K contiguous), bias fp32.  Epilogue selected by `epilogue`:
+ * X, W fp16 row-major (K contiguous, rows 16-byte aligned), bias fp32 (may be NULL).
+ * gather (optional, int64 [rows]): row r of X is read from X[gather[r]], or taken as zero when
+ * gather[r] < 0 -- the masked neighbour gather of net.py:81-85 folded into the operand load.
+ * Epilogues:
  *   DPVO_EPI_NONE      y = acc + bias
  *   DPVO_EPI_RELU      y = relu(acc + bias)
  *   DPVO_EPI_SIGMOID   y = sigmoid(acc + bias)
- *   DPVO_EPI_RESADD    y = res + acc + bias                      (res: [rows, N] res_dtype)
- *   DPVO_EPI_GATEDRES  y = res + gate * (acc + bias)             (gate: [rows, N] fp16)
- * Y dtype y_dtype (F16 or F32).  K % 16 == 0 after caller padding (882 -> 896), N % 16 == 0,
- * N <= 384.  Row tails are handled.
+ *   DPVO_EPI_RESADD    y = res + acc + bias                       (res: [rows, N], F16/F32, stride ldres)
+ *   DPVO_EPI_GATEDRES  y = res + gate * (acc + bias)              (gate: [rows, N] fp16, stride ldgate)
+ * Y dtype y_dtype (F16 or F32), row stride ldy; Y16 (optional) receives an fp16 copy of the same
+ * result (row stride ldy16) so a following layer can consume it without another pass.  Y may alias
+ * res.  K % 64 == 0 (pad 882 -> 896 with zeros), N % 16 == 0.  Row tails are handled.
  */
 #define DPVO_EPI_NONE     0
 #define DPVO_EPI_RELU     1
 #define DPVO_EPI_SIGMOID  2
 #define DPVO_EPI_RESADD   3
 #define DPVO_EPI_GATEDRES 4
-int dpvo_linear_f16(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
-                    const void* res, int res_dtype, const void* gate,
-                    void* Y, int y_dtype, int64_t ldy,
+int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather, const void* W, int64_t ldw,
+                    const float* bias, const void* res, int res_dtype, int64_t ldres,
+                    const void* gate, int64_t ldgate, void* Y, int y_dtype, int64_t ldy,
+                    void* Y16, int64_t ldy16,
                     int64_t rows, int N, int K, int epilogue, void* stream);
 
 #ifdef __cplusplus

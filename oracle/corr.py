@@ -51,6 +51,7 @@ def corr_forward(fmap1, fmap2, coords, ii, jj, radius, chunk=256):
                           for s in range(0, M, chunk)], 1)
     D = 2 * radius + 2
     raw = corr_raw(fmap1, fmap2, coords, ii, jj, radius)
+    # fractions are formed in the dtype of coords (fp32 in DPVO) and only then cast (:221-224)
     x, y = coords[:, :, 0, None, None], coords[:, :, 1, None, None]
     dx = (x - torch.floor(x)).to(fmap1.dtype)
     dy = (y - torch.floor(y)).to(fmap1.dtype)

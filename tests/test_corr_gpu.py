@@ -32,7 +32,7 @@ def _case(seed, M, C=128, S1=40, S2=5, H=30, W=40, dtype=torch.float32, spread=1
 @pytest.mark.parametrize("spread", [1.0, 0.25, 2.7])
 def test_corr_forward_fp32(ext, cl, spread):
     f1, f2, coords, ii, jj, f1d, f2d = _case(1, 300, spread=spread, cl=cl)
-    ref = OC.corr_forward(f1.double(), f2.double(), coords.double(), ii, jj, 3)
+    ref = OC.corr_forward(f1.double(), f2.double(), coords, ii, jj, 3)
     out, = ext[0].forward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
     assert out.shape == ref.shape
     err = (out.cpu().double() - ref).abs().max().item()
@@ -41,7 +41,7 @@ def test_corr_forward_fp32(ext, cl, spread):
 
 def test_corr_forward_fp64(ext):
     f1, f2, coords, ii, jj, f1d, f2d = _case(2, 100, dtype=torch.float64)
-    ref = OC.corr_forward(f1, f2, coords.double(), ii, jj, 3)
+    ref = OC.corr_forward(f1, f2, coords, ii, jj, 3)
     out, = ext[0].forward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
     assert (out.cpu() - ref).abs().max().item() <= 1e-12 * max(1.0, ref.abs().max().item())
 
@@ -53,7 +53,7 @@ def test_corr_forward_fp16(ext, cl, spread):
     rounding of the result (2^-11 relative) plus fp32 accumulation noise -- the reference, which
     accumulates in fp16 (correlation_kernel.cu:121-131), is far outside this bound itself."""
     f1, f2, coords, ii, jj, f1d, f2d = _case(3, 500, dtype=torch.half, spread=spread, cl=cl)
-    ref = OC.corr_forward(f1.double(), f2.double(), coords.double(), ii, jj, 3)
+    ref = OC.corr_forward(f1.double(), f2.double(), coords, ii, jj, 3)
     out, = ext[0].forward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
     err = (out.cpu().double() - ref).abs()
     tol = 2.0 ** -10 * ref.abs() + 1e-4 * ref.abs().max()
@@ -67,7 +67,7 @@ def test_corr_forward_oob_is_zero(ext):
     coords[0, 16:32] -= 1000.0
     out, = ext[0].forward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
     assert float(out[0, :32].abs().max()) == 0.0
-    ref = OC.corr_forward(f1.double(), f2.double(), coords.double(), ii, jj, 3)
+    ref = OC.corr_forward(f1.double(), f2.double(), coords, ii, jj, 3)
     assert (out.cpu().double() - ref).abs().max().item() <= 2.0 ** -9 * ref.abs().max().item()
 
 
@@ -114,7 +114,7 @@ def test_corr_backward_fp32(ext, cl):
     grad = torch.randn(1, 60, 7, 7, 3, 3, generator=g)
     a = f1.double().requires_grad_(True)
     b = f2.double().requires_grad_(True)
-    OC.corr_forward(a, b, coords.double(), ii, jj, 3).backward(grad.double())
+    OC.corr_forward(a, b, coords, ii, jj, 3).backward(grad.double())
     g1, g2 = ext[0].backward(f1d, f2d, coords.to(DEV), ii.to(DEV), jj.to(DEV), grad.to(DEV), 3)
     assert (g1.cpu().double() - a.grad).abs().max().item() <= 2e-5 * a.grad.abs().max().item()
     assert (g2.cpu().double() - b.grad).abs().max().item() <= 2e-5 * b.grad.abs().max().item()

@@ -44,7 +44,7 @@ def test_corr_forward_fp32_three_way(ext, ref):
     args = (f1.to(DEV), f2.to(DEV), coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
     r, = ref[0].forward(*args)
     o, = ext[0].forward(*args)
-    orc = OC.corr_forward(f1.double(), f2.double(), coords.double(), ii, jj, 3)
+    orc = OC.corr_forward(f1.double(), f2.double(), coords, ii, jj, 3)
     s = orc.abs().max().item()
     assert (r.cpu().double() - orc).abs().max().item() <= 2e-6 * s      # oracle == reference kernel
     assert (o.cpu().double() - r.cpu().double()).abs().max().item() <= 2e-6 * s   # ours == reference kernel
@@ -55,7 +55,7 @@ def test_corr_forward_fp16_ours_is_closer_to_exact_than_reference(ext, ref):
     args = (f1.to(DEV), f2.to(DEV), coords.to(DEV), ii.to(DEV), jj.to(DEV), 3)
     r, = ref[0].forward(*args)
     o, = ext[0].forward(*args)
-    orc = OC.corr_forward(f1.double(), f2.double(), coords.double(), ii, jj, 3)
+    orc = OC.corr_forward(f1.double(), f2.double(), coords, ii, jj, 3)
     er = (r.cpu().double() - orc).abs().max().item()
     eo = (o.cpu().double() - orc).abs().max().item()
     s = orc.abs().max().item()
@@ -74,7 +74,7 @@ def test_corr_backward_three_way(ext, ref):
     o1, o2 = ext[0].backward(*args)
     a = f1.double().requires_grad_(True)
     b = f2.double().requires_grad_(True)
-    OC.corr_forward(a, b, coords.double(), ii, jj, 3).backward(grad.double())
+    OC.corr_forward(a, b, coords, ii, jj, 3).backward(grad.double())
     for ours, theirs, orc in ((o1, r1, a.grad), (o2, r2, b.grad)):
         s = orc.abs().max().item()
         assert (theirs.cpu().double() - orc).abs().max().item() <= 3e-5 * s
