@@ -30,11 +30,6 @@ constexpr int BA_CLUSTER = 8;
 constexpr int BA_SOLVE_THREADS = 512;
 constexpr int BA_MAX_FRAMES = 96;     // frame span of the pair lookup table
 
-struct GroupHeaderBA {                // mirror of graph.cu:GroupHeader (ranges of the ij grouping)
-  unsigned barrier; int npass[3];
-  long long amin, amax, bmin, bmax, smin, smax;
-};
-
 struct BaArgs {
   float* poses; float* patches; const float* intrinsics;
   const float* target; const float* weight; const float* lmbda;
@@ -44,7 +39,7 @@ struct BaArgs {
   const int32_t* k_order; const int32_t* k_start; const int64_t* k_key; const int32_t* k_n;
   // ij grouping (pose pairs)
   const int32_t* p_order; const int32_t* p_start; const int64_t* p_key_i; const int64_t* p_key_j;
-  const int32_t* p_n; const GroupHeaderBA* p_hdr;
+  const int32_t* p_n;
   // scratch
   float* Ed;      // [M][6N]
   float* Qk;      // [M]   1/(C+lambda)
@@ -404,8 +399,21 @@ ba_solve_kernel(const BaArgs a) {
   if (N > 0 && rank == 0) {
     // ---- 3. assemble  S = B - E Q E^T,  y = v - E Q u  from the pair records
     const int Gp = *a.p_n;
-    const long long fmin = min(a.p_hdr->amin, a.p_hdr->bmin);
-    const long long fmax = max(a.p_hdr->amax, a.p_hdr->bmax);
+    // frame span of the pair keys (pairs are sorted by (i, j): i range from the ends, j by a scan)
+    __shared__ long long fr[2];
+    if (tid == 0) { fr[0] = a.p_key_i[0]; fr[1] = a.p_key_i[Gp - 1]; }
+    __syncthreads();
+    {
+      long long jmn = 0x7fffffffffffffffLL, jmx = -0x7fffffffffffffffLL - 1;
+      for (int p = tid; p < Gp; p += BA_SOLVE_THREADS) { const long long j = a.p_key_j[p]; jmn = min(jmn, j); jmx = max(jmx, j); }
+      for (int o = 16; o > 0; o >>= 1) {
+        jmn = min(jmn, __shfl_xor_sync(0xffffffffu, jmn, o));
+        jmx = max(jmx, __shfl_xor_sync(0xffffffffu, jmx, o));
+      }
+      if ((tid & 31) == 0) { atomicMin(&fr[0], jmn); atomicMax(&fr[1], jmx); }
+    }
+    __syncthreads();
+    const long long fmin = fr[0], fmax = fr[1];
     const long long span = fmax - fmin + 1;
     const bool use_lut = span <= BA_MAX_FRAMES;
     const int NF = use_lut ? (int)span : 0;
@@ -652,6 +660,59 @@ extern "C" int64_t dpvo_ba_workspace_bytes(int64_t E, int n_free_poses) {
   return ba_ws_layout(E, n_free_poses, nullptr, nullptr) + 256;
 }
 
+static int ba_run(BaArgs& a, int iterations, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveSmem));
+    if (e != cudaSuccess) return check_cuda(e, "ba_forward: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  const int red_blocks = sm_count() * 4;
+  for (int it = 0; it < iterations; ++it) {
+    ba_reduce_kernel<<<red_blocks, BA_RED_WARPS * 32, 0, st>>>(a);
+    DPVO_LAUNCH_CHECK("ba_reduce_kernel");
+    ba_solve_kernel<<<BA_CLUSTER, BA_SOLVE_THREADS, sizeof(SolveSmem), st>>>(a);
+    DPVO_LAUNCH_CHECK("ba_solve_kernel");
+  }
+  return DPVO_OK;
+}
+
+extern "C" int64_t dpvo_ba_grouped_workspace_bytes(int64_t E, int n_free_poses) {
+  if (E < 0) E = 0;
+  return al256(E * 6 * (int64_t)std::max(n_free_poses, 1) * 4) + 2 * al256(E * 4) + al256(E * (int64_t)BA_REC * 4) +
+         al256(6 * BA_MAX_N * 4) + 512;
+}
+
+extern "C" int dpvo_ba_forward_grouped(float* poses, float* patches, const float* intrinsics,
+                                       const float* target, const float* weight, const float* lmbda,
+                                       const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                                       int64_t E, int P, int t0, int t1, int iterations,
+                                       const int32_t* k_order, const int32_t* k_start, const int64_t* k_key, const int32_t* k_n,
+                                       const int32_t* p_order, const int32_t* p_start, const int64_t* p_key_i,
+                                       const int64_t* p_key_j, const int32_t* p_n,
+                                       void* workspace, int64_t workspace_bytes, void* stream) {
+  DPVO_REQUIRE(E >= 0 && P > 0 && iterations >= 0 && t1 >= t0, "ba_forward_grouped: bad sizes");
+  if (E == 0 || iterations == 0) return DPVO_OK;
+  DPVO_REQUIRE(poses && patches && intrinsics && target && weight && lmbda && ii && jj && kk && workspace && k_order &&
+               k_start && k_key && k_n, "ba_forward_grouped: null pointer");
+  const int N = t1 - t0;
+  DPVO_REQUIRE(N == 0 || (p_order && p_start && p_key_i && p_key_j && p_n), "ba_forward_grouped: pair grouping missing");
+  if (N > BA_MAX_N) { set_error("ba_forward_grouped: %d free poses > %d", N, BA_MAX_N); return DPVO_ERR_UNSUPPORTED; }
+  if (workspace_bytes < dpvo_ba_grouped_workspace_bytes(E, N)) { set_error("ba_forward_grouped: workspace too small"); return DPVO_ERR_WORKSPACE; }
+  char* p = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  BaArgs a;
+  a.poses = poses; a.patches = patches; a.intrinsics = intrinsics; a.target = target; a.weight = weight;
+  a.lmbda = lmbda; a.ii = ii; a.jj = jj; a.kk = kk; a.E = E; a.P = P; a.t0 = t0; a.N = N;
+  a.k_order = k_order; a.k_start = k_start; a.k_key = k_key; a.k_n = k_n;
+  a.p_order = p_order; a.p_start = p_start; a.p_key_i = p_key_i; a.p_key_j = p_key_j; a.p_n = p_n;
+  a.Ed = (float*)p; p += al256(E * 6 * (int64_t)std::max(N, 1) * 4);
+  a.Qk = (float*)p; p += al256(E * 4);
+  a.uk = (float*)p; p += al256(E * 4);
+  a.rec = (float*)p; p += al256(E * (int64_t)BA_REC * 4);
+  a.dX = (float*)p;
+  return ba_run(a, iterations, (cudaStream_t)stream);
+}
+
 extern "C" int dpvo_ba_forward(float* poses, float* patches, const float* intrinsics,
                                const float* target, const float* weight, const float* lmbda,
                                const int64_t* ii, const int64_t* jj, const int64_t* kk,
@@ -692,23 +753,8 @@ extern "C" int dpvo_ba_forward(float* poses, float* patches, const float* intrin
   a.lmbda = lmbda; a.ii = ii; a.jj = jj; a.kk = kk; a.E = E; a.P = P; a.t0 = t0; a.N = N;
   a.k_order = w.k_order; a.k_start = w.k_start; a.k_key = w.k_key; a.k_n = w.k_n;
   a.p_order = w.p_order; a.p_start = w.p_start; a.p_key_i = w.p_key_i; a.p_key_j = w.p_key_j; a.p_n = w.p_n;
-  a.p_hdr = (const GroupHeaderBA*)w.gws_p;
   a.Ed = w.Ed; a.Qk = w.Qk; a.uk = w.uk; a.rec = w.rec; a.dX = w.dX;
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveSmem));
-    if (e != cudaSuccess) return check_cuda(e, "ba_forward: cudaFuncSetAttribute");
-    attr_set = true;
-  }
-  const int red_blocks = sm_count() * 4;
-  for (int it = 0; it < iterations; ++it) {
-    ba_reduce_kernel<<<red_blocks, BA_RED_WARPS * 32, 0, st>>>(a);
-    DPVO_LAUNCH_CHECK("ba_reduce_kernel");
-    ba_solve_kernel<<<BA_CLUSTER, BA_SOLVE_THREADS, sizeof(SolveSmem), st>>>(a);
-    DPVO_LAUNCH_CHECK("ba_solve_kernel");
-  }
-  return DPVO_OK;
+  return ba_run(a, iterations, st);
 }
 
 extern "C" int dpvo_reproject(const float* poses, const float* patches, const float* intrinsics,

@@ -234,23 +234,34 @@ __device__ __forceinline__ uint4 ldg128(const void* p) {
 
 constexpr int MMA_WARPS = 8;
 constexpr int MMA_PATP = 136;   // halves per patch-pixel row in shared (128 + 8 pad)
-constexpr int MMA_RAWP = 65;    // floats per pixel in the raw tap tile (64 + 1 pad)
 constexpr int MMA_BOX = 10;
+constexpr int MMA_RAWP = 105;   // floats per patch pixel in the raw tile (odd pitch: conflict-free)
 
+// per-warp shared memory: the patch staging buffer is dead once the A fragments are in registers,
+// so the raw tap tile aliases it
 struct __align__(16) MmaWarpSmem {
-  __half patch[9 * MMA_PATP];
-  float raw[9 * MMA_RAWP];
-  float fx[9], fy[9];
-  int ax[9], ay[9];
+  union {
+    __half patch[9 * MMA_PATP];       // 2448 B
+    float raw[2][9 * MMA_RAWP + 3];   // per level: raw[p][box pixel] = <patch pixel p, box pixel>
+  };
+  float4 w[2][9];                     // bilinear weights (1-dx)(1-dy), dx(1-dy), (1-dx)dy, dx dy
+  int base[2][9];                     // index of tap (0,0) of pixel p inside its box
+  int pitch[2][9];                    // row pitch of that box (bw, or 8 in the per-pixel fallback)
 };
 
 // C = 128, P = 3, R = 3 (D = 8), fp16, fmap2 channels-last with 16-byte aligned pixels.
+// Instruction budget matters more than bytes here (the first version issued 10k instructions per
+// edge, 34 % of them integer multiply-adds from divisions and 64-bit address arithmetic):
+//   * box coordinates advance incrementally per 8-pixel tile (no division in the loops)
+//   * accumulators are stored densely as raw[p][box pixel]; the bilinear stage indexes the box
+//   * per-lane output decomposition (q -> p, x-off, y-off) is computed once per kernel
+//   * two independent HMMA accumulation chains per tile halve the dependent-issue latency
 template <bool PAIR_OUT>
 __global__ void __launch_bounds__(MMA_WARPS * 32, 2)
 corr_fwd_mma(const CorrArgs a) {
   constexpr int D = 8, O = 7, NOUT = O * O * 9;   // 441
-  __shared__ MmaWarpSmem sm_all[MMA_WARPS];
-  MmaWarpSmem& sm = sm_all[threadIdx.x >> 5];
+  extern __shared__ __align__(16) unsigned char mma_smem_raw[];
+  MmaWarpSmem& sm = reinterpret_cast<MmaWarpSmem*>(mma_smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t nitems = (int64_t)a.B * a.M;
   const int64_t wstride = (int64_t)gridDim.x * MMA_WARPS;
@@ -262,6 +273,7 @@ corr_fwd_mma(const CorrArgs a) {
     const int64_t ix = a.ii[m], jx = a.jj[m];
 
     // ---- patch features -> shared as [pixel][channel]
+    __syncwarp();
     {
       const __half* src = f1 + b * a.s1[0] + ix * a.s1[1];
       if (a.s1[2] == 1 && (a.s1[3] % 8 == 0) && (a.s1[4] % 8 == 0)) {
@@ -288,109 +300,112 @@ corr_fwd_mma(const CorrArgs a) {
       PB[kb] = (g == 0) ? *reinterpret_cast<const uint4*>(&sm.patch[8 * MMA_PATP + kb * 32 + t * 8])
                         : make_uint4(0u, 0u, 0u, 0u);
     }
-
-    float keep[PAIR_OUT ? 14 : 1];   // level-0 results when both levels are written as pairs
+    __syncwarp();                      // patch buffer is dead from here on (raw aliases it)
 
     for (int lev = 0; lev < a.nlev; ++lev) {
+      float* raw = sm.raw[lev];
       const __half* f2 = reinterpret_cast<const __half*>(a.fmap2[lev]) + b * a.s2[lev][0] + jx * a.s2[lev][1];
-      const int64_t sy = a.s2[lev][3], sx = a.s2[lev][4];
+      const int sy = (int)a.s2[lev][3], sx = (int)a.s2[lev][4];     // element strides inside one frame (< 2^31)
       const int H2 = a.H2[lev], W2 = a.W2[lev];
 
-      // ---- anchors / fractions of the nine patch pixels
+      // ---- anchors / fractions of the nine patch pixels (lanes 0..8)
       int ax = 1 << 28, ay = 1 << 28, axm = -(1 << 28), aym = -(1 << 28);
+      float fx = 0.f, fy = 0.f;
       if (lane < 9) {
         const float* cp = a.coords + ((int64_t)(b * a.M + m) * 2) * 9;
         float x = cp[lane], y = cp[9 + lane];
         if (a.div[lev] != 1.0f) { x = x / a.div[lev]; y = y / a.div[lev]; }
         ax = safe_floor_int(x) - 3; ay = safe_floor_int(y) - 3;
         axm = ax; aym = ay;
-        sm.ax[lane] = ax; sm.ay[lane] = ay;
-        sm.fx[lane] = x - floorf(x); sm.fy[lane] = y - floorf(y);
+        fx = x - floorf(x); fy = y - floorf(y);
       }
       const int bx_min = warp_min_i(ax), by_min = warp_min_i(ay);
       const int bx_max = warp_max_i(axm), by_max = warp_max_i(aym);
       const bool uni = (bx_max - bx_min + D <= MMA_BOX) && (by_max - by_min + D <= MMA_BOX);
-      __syncwarp();
-      // anchors of the two accumulator rows this lane owns: pixel g and pixel 8
-      const int pax_g = sm.ax[g], pay_g = sm.ay[g], pax_8 = sm.ax[8], pay_8 = sm.ay[8];
+      const int ubw = bx_max - bx_min + D;
+      if (lane < 9) {
+        sm.w[lev][lane] = make_float4((1.f - fx) * (1.f - fy), fx * (1.f - fy), (1.f - fx) * fy, fx * fy);
+        sm.base[lev][lane] = uni ? (ay - by_min) * ubw + (ax - bx_min) : 0;
+        sm.pitch[lev][lane] = uni ? ubw : D;
+      }
 
       const int npass = uni ? 1 : 9;
       for (int pass = 0; pass < npass; ++pass) {
-        const int bx0 = uni ? bx_min : sm.ax[pass];
-        const int by0 = uni ? by_min : sm.ay[pass];
-        const int bw = uni ? (bx_max - bx_min + D) : D;
-        const int bh = uni ? (by_max - by_min + D) : D;
-        const int rows = bw * bh;
+        const int bx0 = uni ? bx_min : __shfl_sync(0xffffffffu, ax, pass);
+        const int by0 = uni ? by_min : __shfl_sync(0xffffffffu, ay, pass);
+        const int bw = uni ? ubw : D;
+        const int rows = uni ? ubw * (by_max - by_min + D) : D * D;
         const int ntiles = (rows + 7) >> 3;
 
-        auto load_tile = [&](int nt, uint4 (&Q)[4]) {
-          const int wp = nt * 8 + g;
-          const int wy = wp / bw, wx = wp - wy * bw;
+        // box pixel of this lane's B-operand column: wp = nt*8 + g, advanced incrementally
+        int wx = g, wy = 0;
+        if (wx >= bw) { wx -= bw; wy = 1; }
+        auto load_tile = [&](uint4 (&Q)[4], int wp) {
           const int y = by0 + wy, x = bx0 + wx;
-          const bool ok = (wp < rows) && (y >= 0) && (y < H2) && (x >= 0) && (x < W2);
+          const bool ok = (wp < rows) && ((unsigned)y < (unsigned)H2) && ((unsigned)x < (unsigned)W2);
           if (ok) {
-            const __half* p = f2 + (int64_t)y * sy + (int64_t)x * sx + t * 8;
+            const __half* p = f2 + (y * sy + x * sx + t * 8);
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) Q[kb] = ldg128(p + kb * 32);
           } else {
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) Q[kb] = make_uint4(0u, 0u, 0u, 0u);
           }
+          wx += 8; if (wx >= bw) { wx -= bw; ++wy; }          // 8 <= bw <= 10: at most one wrap
         };
 
         uint4 Qc[4], Qn[4];
-        load_tile(0, Qc);
+        load_tile(Qc, g);
         for (int nt = 0; nt < ntiles; ++nt) {
-          if (nt + 1 < ntiles) load_tile(nt + 1, Qn);
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          if (nt + 1 < ntiles) load_tile(Qn, (nt + 1) * 8 + g);
+          float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
-            mma16816(acc, PA[kb].x, PB[kb].x, PA[kb].y, PB[kb].y, Qc[kb].x, Qc[kb].y);
-            mma16816(acc, PA[kb].z, PB[kb].z, PA[kb].w, PB[kb].w, Qc[kb].z, Qc[kb].w);
+            mma16816(acc0, PA[kb].x, PB[kb].x, PA[kb].y, PB[kb].y, Qc[kb].x, Qc[kb].y);
+            mma16816(acc1, PA[kb].z, PB[kb].z, PA[kb].w, PB[kb].w, Qc[kb].z, Qc[kb].w);
           }
-          // acc[0],acc[1]: pixel g  x box pixels nt*8+2t, +1 ; acc[2],acc[3]: pixel 8 (g==0 lanes)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int wp = nt * 8 + 2 * t + j;
-            if (wp < rows) {
-              const int wy = wp / bw, wx = wp - wy * bw;
-              if (uni || pass == g) {
-                const int ty = wy - (pay_g - by0), tx = wx - (pax_g - bx0);
-                if (ty >= 0 && ty < D && tx >= 0 && tx < D) sm.raw[g * MMA_RAWP + ty * D + tx] = acc[j];
-              }
-              if (g == 0 && (uni || pass == 8)) {
-                const int ty = wy - (pay_8 - by0), tx = wx - (pax_8 - bx0);
-                if (ty >= 0 && ty < D && tx >= 0 && tx < D) sm.raw[8 * MMA_RAWP + ty * D + tx] = acc[2 + j];
-              }
-            }
-          }
+          // rows of the accumulator tile = patch pixels g (c0,c1) and 8 (c2,c3; g==0 lanes);
+          // columns = box pixels nt*8 + 2t, +1: stored densely, no per-tap logic
+          const int col = nt * 8 + 2 * t;
+          if (uni || g == pass)
+            *reinterpret_cast<float2*>(&raw[g * MMA_RAWP + col + (g & 1)]) = make_float2(acc0[0] + acc1[0], acc0[1] + acc1[1]);
+          if (g == 0 && (uni || pass == 8))
+            *reinterpret_cast<float2*>(&raw[8 * MMA_RAWP + col]) = make_float2(acc0[2] + acc1[2], acc0[3] + acc1[3]);
           if (nt + 1 < ntiles) {
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) Qc[kb] = Qn[kb];
           }
         }
       }
-      __syncwarp();
+    }
+    __syncwarp();
 
-      // ---- bilinear blend + write
+    // ---- bilinear blend of both levels + write (q = output element, p = q % 9, tap = q / 9)
+#pragma unroll 2
+    for (int i = 0; i < 14; ++i) {
+      const int q = lane + 32 * i;
+      if (q < NOUT) {
+        const int tt = (q * 3641) >> 15;            // q / 9 for q < 4096
+        const int p = q - 9 * tt;
+        const int xo = (tt * 37) >> 8;              // tt / 7 for tt < 56
+        const int yo = tt - 7 * xo;
+        float v[2];
 #pragma unroll
-      for (int i = 0; i < 14; ++i) {
-        const int q = lane + 32 * i;
-        if (q < NOUT) {
-          const int p = q % 9, tt = q / 9, yo = tt % O, xo = tt / O;
-          const float dx = sm.fx[p], dy = sm.fy[p];
-          const float* rp = &sm.raw[p * MMA_RAWP + yo * D + xo];
-          const float v = (1.f - dx) * (1.f - dy) * rp[0] + dx * (1.f - dy) * rp[1] +
-                          (1.f - dx) * dy * rp[D] + dx * dy * rp[D + 1];
-          if constexpr (PAIR_OUT) {
-            if (lev == 0) keep[i] = v;
-            else reinterpret_cast<__half2*>(out + (int64_t)(b * a.M + m) * a.out_row)[q] = __floats2half2_rn(keep[i], v);
-          } else {
-            out[(int64_t)(b * a.M + m) * a.out_row + (int64_t)q * a.out_stride + a.out_offset[lev]] = __float2half_rn(v);
+        for (int lev = 0; lev < 2; ++lev) {
+          if (lev < a.nlev) {
+            const int pitch = sm.pitch[lev][p];
+            const float4 w = sm.w[lev][p];
+            const float* rp = &sm.raw[lev][p * MMA_RAWP + (p & 1) + sm.base[lev][p] + yo * pitch + xo];
+            v[lev] = w.x * rp[0] + w.y * rp[1] + w.z * rp[pitch] + w.w * rp[pitch + 1];
           }
         }
+        if constexpr (PAIR_OUT) {
+          reinterpret_cast<__half2*>(out + (int64_t)(b * a.M + m) * a.out_row)[q] = __floats2half2_rn(v[0], v[1]);
+        } else {
+          for (int lev = 0; lev < a.nlev; ++lev)
+            out[(int64_t)(b * a.M + m) * a.out_row + (int64_t)q * a.out_stride + a.out_offset[lev]] = __float2half_rn(v[lev]);
+        }
       }
-      __syncwarp();
     }
   }
 }
@@ -647,8 +662,15 @@ static int launch_mma(const CorrArgs& a, bool pair_out, cudaStream_t st) {
   if (nitems == 0) return DPVO_OK;
   const int64_t need = (nitems + MMA_WARPS - 1) / MMA_WARPS;
   const int64_t grid = std::min<int64_t>(need, (int64_t)sm_count() * 2);
-  if (pair_out) corr_fwd_mma<true><<<(unsigned)grid, MMA_WARPS * 32, 0, st>>>(a);
-  else corr_fwd_mma<false><<<(unsigned)grid, MMA_WARPS * 32, 0, st>>>(a);
+  const size_t smem = sizeof(MmaWarpSmem) * MMA_WARPS;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(corr_fwd_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(corr_fwd_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  if (pair_out) corr_fwd_mma<true><<<(unsigned)grid, MMA_WARPS * 32, smem, st>>>(a);
+  else corr_fwd_mma<false><<<(unsigned)grid, MMA_WARPS * 32, smem, st>>>(a);
   DPVO_LAUNCH_CHECK("corr_fwd_mma");
   return DPVO_OK;
 }

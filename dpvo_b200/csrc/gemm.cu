@@ -24,7 +24,7 @@ constexpr int GM_N = 192;            // columns per tile (UMMA N, multiple of 16
 constexpr int GM_K = 64;             // halves per k-block: 128 bytes, one swizzle atom
 constexpr int GM_UK = 16;            // UMMA K for 16-bit operands
 constexpr int GM_STAGES = 5;
-constexpr int GM_LOOK = 2;           // cp.async groups kept in flight per producer thread
+constexpr int GM_LOOK = 4;           // cp.async groups kept in flight per producer thread (< GM_STAGES)
 constexpr int GM_EPI_THREADS = 128, GM_PROD_THREADS = 128;
 constexpr int GM_THREADS = GM_EPI_THREADS + 32 + GM_PROD_THREADS;
 constexpr int GM_A_BYTES = GM_M * 128, GM_B_BYTES = GM_N * 128;
@@ -96,6 +96,7 @@ constexpr uint32_t GM_IDESC = (1u << 4) | ((uint32_t)(GM_N >> 3) << 17) | ((uint
 struct GemmBars {
   uint64_t full[GM_STAGES], empty[GM_STAGES], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
+  float bias[4][GM_N];          // per epilogue warp: bias of the current column tile
 };
 
 __device__ __forceinline__ float epi_act(float v, int epi) {
@@ -211,6 +212,10 @@ linear_f16_kernel(const GemmArgs a) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       const int64_t row = (tile / n_tiles_n) * GM_M + row_in_tile;
       const int n0 = (int)(tile % n_tiles_n) * GM_N;
+      // bias of this column tile -> shared (per warp, so only a warp-level sync is needed)
+      float* sbias = bars->bias[warp];
+      for (int j = lane; j < GM_N; j += 32) sbias[j] = (a.bias && n0 + j < a.N) ? a.bias[n0 + j] : 0.f;
+      __syncwarp();
       mbar_wait(&bars->tmem_full[acc], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * GM_N;
@@ -224,7 +229,7 @@ linear_f16_kernel(const GemmArgs a) {
         if (row_ok && col < a.N) {
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (a.bias ? a.bias[col + j] : 0.f);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + sbias[c0 + j];
           if (a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -262,6 +267,7 @@ linear_f16_kernel(const GemmArgs a) {
       }
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[acc]);
+      __syncwarp();
     }
   }
 

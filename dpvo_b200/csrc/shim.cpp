@@ -306,6 +306,30 @@ std::vector<Tensor> group_edges(Tensor key_a, c10::optional<Tensor> key_b, c10::
   return {order, gof, gstart, ka, kbo, ng};
 }
 
+// fastba.BA on groupings built once per update (order, group_start, key_a[, key_b], n of EdgeGroups)
+void ba_forward_grouped(Tensor poses, Tensor patches, Tensor intrinsics, Tensor target, Tensor weight, Tensor lmbda,
+                        Tensor ii, Tensor jj, Tensor kk, int t0, int t1, int iterations,
+                        Tensor k_order, Tensor k_start, Tensor k_key, Tensor k_n,
+                        Tensor p_order, Tensor p_start, Tensor p_key_i, Tensor p_key_j, Tensor p_n) {
+  need_cuda(poses, "poses"); need_cuda(patches, "patches");
+  c10::cuda::CUDAGuard guard(poses.device());
+  TORCH_CHECK(poses.is_contiguous() && patches.is_contiguous(), "ba_forward_grouped updates poses/patches in place: they must be contiguous");
+  TORCH_CHECK(poses.scalar_type() == at::kFloat && patches.scalar_type() == at::kFloat, "ba_forward_grouped: poses/patches must be float32");
+  const int P = patches.size(-1);
+  intrinsics = f32c(intrinsics); target = f32c(target); weight = f32c(weight); lmbda = f32c(lmbda);
+  ii = i64c(ii); jj = i64c(jj); kk = i64c(kk);
+  const int64_t E = ii.numel();
+  const int64_t wsb = dpvo_ba_grouped_workspace_bytes(E, t1 - t0);
+  Tensor ws = byte_ws(wsb, poses);
+  check(dpvo_ba_forward_grouped(poses.data_ptr<float>(), patches.data_ptr<float>(), intrinsics.data_ptr<float>(),
+                                target.data_ptr<float>(), weight.data_ptr<float>(), lmbda.data_ptr<float>(),
+                                ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), kk.data_ptr<int64_t>(), E, P, t0, t1, iterations,
+                                k_order.data_ptr<int>(), k_start.data_ptr<int>(), k_key.data_ptr<int64_t>(), k_n.data_ptr<int>(),
+                                p_order.data_ptr<int>(), p_start.data_ptr<int>(), p_key_i.data_ptr<int64_t>(),
+                                p_key_j.data_ptr<int64_t>(), p_n.data_ptr<int>(), ws.data_ptr(), wsb, stream()),
+        "dpvo_b200_ext.ba_forward_grouped");
+}
+
 Tensor reproject_clamped(Tensor poses, Tensor patches, Tensor intrinsics, Tensor ii, Tensor jj, Tensor kk) {
   return reproject_impl(poses, patches, intrinsics, ii, jj, kk, 1);
 }
@@ -502,6 +526,7 @@ PYBIND11_MODULE(dpvo_b200_ext, m) {
         py::arg("coords"), py::arg("ii"), py::arg("jj"), py::arg("radius"), py::arg("div"), py::arg("pad_to") = 0);
   m.def("group_edges", &group_edges, "device edge grouping", py::arg("key_a"), py::arg("key_b") = py::none(),
         py::arg("sec") = py::none());
+  m.def("ba_forward_grouped", &ba_forward_grouped, "fastba.BA on prebuilt edge groupings");
   m.def("reproject_clamped", &reproject_clamped, "pops.transform-compatible fused reprojection");
   m.def("add_layernorm", &add_layernorm, "fused add + LayerNorm (+ReLU)");
   m.def("gather_rows_masked", &gather_rows_masked, "masked row gather");

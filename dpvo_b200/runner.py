@@ -66,8 +66,8 @@ class UpdateRunner:
         target = coords[:, :, :, 1, 1] + delta
         if ev is not None:
             ev["ba0"].record()
-        fastba.BA(poses, patches, intr, target, weight, self.lmbda, s.ii, s.jj, s.kk, s.t0, s.n, self.M,
-                  self.ba_iterations, False)
+        fastba.BA_grouped(poses, patches, intr, target, weight, self.lmbda, s.ii, s.jj, s.kk, s.t0, s.n,
+                          self.ba_iterations, groups_kk, groups_ij)
         if ev is not None:
             ev["ba1"].record()
         return target, weight

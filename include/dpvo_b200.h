@@ -198,6 +198,22 @@ int dpvo_ba_forward(float* poses, float* patches, const float* intrinsics,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * Same Gauss-Newton iterations on groupings the caller already holds (the update operator builds
+ * exactly these two per update): kk grouping = dpvo_group_edges(kk, NULL, [jj]) -> k_order, k_start,
+ * k_key (= sorted unique patch ids), k_n;  pair grouping = dpvo_group_edges(ii, jj, NULL) -> p_order,
+ * p_start, p_key_i, p_key_j, p_n.  workspace: dpvo_ba_grouped_workspace_bytes(E, t1 - t0).
+ */
+int64_t dpvo_ba_grouped_workspace_bytes(int64_t E, int n_free_poses);
+int dpvo_ba_forward_grouped(float* poses, float* patches, const float* intrinsics,
+                            const float* target, const float* weight, const float* lmbda,
+                            const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                            int64_t E, int P, int t0, int t1, int iterations,
+                            const int32_t* k_order, const int32_t* k_start, const int64_t* k_key, const int32_t* k_n,
+                            const int32_t* p_order, const int32_t* p_start, const int64_t* p_key_i,
+                            const int64_t* p_key_j, const int32_t* p_n,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * cuda_ba.reproject -- ba_cuda.cu:585-617 (kernel :379-429): coords fp32 [E, 2, P, P].
  * clamp_depth = 0 reproduces the kernel (divide by raw Z, :422-423, intrinsics row 0);
  * clamp_depth = 1 reproduces pops.transform (projective_ops.py:53-68: Z clamped to >= 0.1 in
