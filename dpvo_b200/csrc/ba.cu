@@ -28,7 +28,6 @@ constexpr int BA_MAX_N = 32;          // free poses held on chip
 constexpr int BA_REC = 90;            // floats per pair record
 constexpr int BA_CLUSTER = 8;
 constexpr int BA_SOLVE_THREADS = 512;
-constexpr int BA_MAX_FRAMES = 96;     // frame span of the pair lookup table
 
 struct BaArgs {
   float* poses; float* patches; const float* intrinsics;
@@ -309,39 +308,46 @@ ba_reduce_kernel(const BaArgs a) {
 // ==========================================================================================
 // kernel B: Schur complement, solve, retraction -- one thread-block cluster
 // ==========================================================================================
-__device__ __forceinline__ int tri_index(int x, int y) {   // upper triangle of a 6x6 block, x <= y
-  return x * 6 - (x * (x - 1)) / 2 + (y - x);
-}
+constexpr int BA_LD = 6 * BA_MAX_N + 1;       // leading dimension (odd: conflict-free columns); row N6 = rhs
+constexpr int BA_REC_CHUNK = 64;              // pair records staged per round
 
 struct SolveSmem {
-  float S[6 * BA_MAX_N][6 * BA_MAX_N + 1];   // Schur partial, then the full system (CTA 0)
-  float y[6 * BA_MAX_N];
+  float S[BA_LD][BA_LD];                      // upper triangle while accumulating, lower triangle for the factor
   float dx[6 * BA_MAX_N];
-  float Et[32][6 * BA_MAX_N + 1];            // tile of E rows
+  union {
+    float Et[32][BA_LD];                      // tile of E rows (Schur phase)
+    float recs[BA_REC_CHUNK][BA_REC];         // pair records (assembly phase)
+  };
   float Qt[32], Ut[32];
-  int lut[BA_MAX_FRAMES * BA_MAX_FRAMES];    // (frame_i - fmin, frame_j - fmin) -> pair id + 1
+  int rec_i[BA_REC_CHUNK], rec_j[BA_REC_CHUNK];
 };
 
+// One thread-block cluster per Gauss-Newton iteration:
+//   1. every CTA: - sum_k Q_k E_k E_k^T (2x2 register micro-tiles) and - sum_k Q_k u_k E_k over its
+//      slice of the patches, then + the 6x6 pose blocks of its share of the (i,j) pair records
+//   2. CTA 0 sums the 8 partial systems over distributed shared memory in rank order
+//   3. CTA 0: damping, blocked (6x6) right-looking Cholesky of the rhs-augmented matrix -- the forward
+//      substitution falls out of the factorisation -- and a one-warp back substitution
+//   4. every CTA: depth updates dZ = Q (u - E^T dX) for its patches (one warp per patch, coalesced),
+//      patch retraction; CTA 0: SE3 retraction of the free poses
 __global__ void __cluster_dims__(BA_CLUSTER, 1, 1) __launch_bounds__(BA_SOLVE_THREADS, 1)
 ba_solve_kernel(const BaArgs a) {
   extern __shared__ __align__(16) unsigned char solve_smem_raw[];
   SolveSmem& sm = *reinterpret_cast<SolveSmem*>(solve_smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N, N6 = 6 * N;
   const int Gk = *a.k_n;
   const int P = a.P;
-
-  // patches of this CTA: contiguous slice [m0, m1)
   const int per = (Gk + BA_CLUSTER - 1) / BA_CLUSTER;
   const int m0 = min(Gk, rank * per), m1 = min(Gk, m0 + per);
 
   if (N > 0) {
-    // ---- 1. partial Schur products over this CTA's patches (upper triangle + rhs column)
-    for (int o = tid; o < N6 * N6; o += BA_SOLVE_THREADS) sm.S[o / N6][o % N6] = 0.0f;
-    for (int i = tid; i < N6; i += BA_SOLVE_THREADS) sm.y[i] = 0.0f;
+    for (int o = tid; o < (N6 + 1) * N6; o += BA_SOLVE_THREADS) sm.S[o / N6][o % N6] = 0.0f;
     __syncthreads();
+    // ---- 1a. Schur products over this CTA's patches
+    const int H = N6 / 2, n_micro = H * (H + 1) / 2;
     for (int mbase = m0; mbase < m1; mbase += 32) {
       const int cnt = min(32, m1 - mbase);
       for (int i = tid; i < cnt * N6; i += BA_SOLVE_THREADS) {
@@ -350,19 +356,79 @@ ba_solve_kernel(const BaArgs a) {
       }
       if (tid < cnt) { sm.Qt[tid] = a.Qk[mbase + tid]; sm.Ut[tid] = a.uk[mbase + tid]; }
       __syncthreads();
-      // every thread owns fixed (row, col) entries, so no atomics are needed
-      for (int o = tid; o < N6 * N6 + N6; o += BA_SOLVE_THREADS) {
-        if (o < N6 * N6) {
-          const int row = o / N6, col = o - row * N6;
-          if (row > col) continue;
-          float s = 0.0f;
-          for (int k = 0; k < cnt; ++k) s += sm.Qt[k] * sm.Et[k][row] * sm.Et[k][col];
-          sm.S[row][col] += s;
+      for (int mt = tid; mt < n_micro + N6; mt += BA_SOLVE_THREADS) {
+        if (mt < n_micro) {
+          int r2 = 0, rem = mt;
+          while (rem >= H - r2) { rem -= H - r2; ++r2; }
+          const int c2 = r2 + rem;
+          float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+          for (int k = 0; k < cnt; ++k) {
+            const float q = sm.Qt[k];
+            const float e0 = q * sm.Et[k][2 * r2], e1 = q * sm.Et[k][2 * r2 + 1];
+            const float f0 = sm.Et[k][2 * c2], f1 = sm.Et[k][2 * c2 + 1];
+            a00 += e0 * f0; a01 += e0 * f1; a10 += e1 * f0; a11 += e1 * f1;
+          }
+          sm.S[2 * r2][2 * c2] -= a00; sm.S[2 * r2][2 * c2 + 1] -= a01;
+          sm.S[2 * r2 + 1][2 * c2 + 1] -= a11;
+          if (r2 != c2) sm.S[2 * r2 + 1][2 * c2] -= a10;
         } else {
-          const int row = o - N6 * N6;
+          const int row = mt - n_micro;
           float s = 0.0f;
           for (int k = 0; k < cnt; ++k) s += sm.Qt[k] * sm.Ut[k] * sm.Et[k][row];
-          sm.y[row] += s;
+          sm.S[N6][row] -= s;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- 1b. pose blocks from this CTA's share of the pair records (pairs rank, rank+8, ...)
+    const int Gp = *a.p_n;
+    const int n_mine = (Gp > rank) ? (Gp - rank + BA_CLUSTER - 1) / BA_CLUSTER : 0;
+    for (int c0 = 0; c0 < n_mine; c0 += BA_REC_CHUNK) {
+      const int cn = min(BA_REC_CHUNK, n_mine - c0);
+      for (int i = tid; i < cn * BA_REC; i += BA_SOLVE_THREADS) {
+        const int r = i / BA_REC, e = i - r * BA_REC;
+        sm.recs[r][e] = a.rec[(int64_t)(rank + (int64_t)(c0 + r) * BA_CLUSTER) * BA_REC + e];
+      }
+      if (tid < cn) {
+        const int p = rank + (c0 + tid) * BA_CLUSTER;
+        long long fi = a.p_key_i[p] - a.t0, fj = a.p_key_j[p] - a.t0;
+        sm.rec_i[tid] = (fi >= 0 && fi < N) ? (int)fi : -1;
+        sm.rec_j[tid] = (fj >= 0 && fj < N) ? (int)fj : -1;
+      }
+      __syncthreads();
+      if (tid < 96) {
+        // targets of one record are distinct; records are applied one after the other (fixed order)
+        for (int r = 0; r < cn; ++r) {
+          const int bi = sm.rec_i[r], bj = sm.rec_j[r];
+          const float* rc = sm.recs[r];
+          if (tid < 21) {                                  // J_i J_i^T  -> block (i,i), upper triangle
+            if (bi >= 0) {
+              int x = 0, rem = tid;
+              while (rem >= 6 - x) { rem -= 6 - x; ++x; }
+              const int y = x + rem;
+              float v = rc[tid];
+              if (bi == bj) v += rc[57 + tid] + rc[21 + x * 6 + y] + rc[21 + y * 6 + x];   // self edge i -> i
+              sm.S[6 * bi + x][6 * bi + y] += v;
+            }
+          } else if (tid < 42) {                           // J_j J_j^T  -> block (j,j)
+            if (bj >= 0 && bi != bj) {
+              const int e = tid - 21;
+              int x = 0, rem = e;
+              while (rem >= 6 - x) { rem -= 6 - x; ++x; }
+              sm.S[6 * bj + x][6 * bj + x + rem] += rc[57 + e];
+            }
+          } else if (tid < 78) {                           // -J_i J_j^T -> block (i,j) or its transpose
+            if (bi >= 0 && bj >= 0 && bi != bj) {
+              const int e = tid - 42, x = e / 6, y = e - 6 * x;
+              if (bi < bj) sm.S[6 * bi + x][6 * bj + y] += rc[21 + e];
+              else sm.S[6 * bj + y][6 * bi + x] += rc[21 + e];
+            }
+          } else if (tid < 84) {                           // gradient, pose i (and j for a self edge)
+            if (bi >= 0) sm.S[N6][6 * bi + tid - 78] += rc[tid] + ((bi == bj) ? rc[tid + 6] : 0.0f);
+          } else if (tid < 90) {                           // gradient, pose j
+            if (bj >= 0 && bi != bj) sm.S[N6][6 * bj + tid - 84] += rc[tid];
+          }
+          asm volatile("bar.sync 1, 96;\n" ::: "memory");
         }
       }
       __syncthreads();
@@ -371,160 +437,69 @@ ba_solve_kernel(const BaArgs a) {
   cluster.sync();
 
   if (N > 0 && rank == 0) {
-    // ---- 2. fixed-order reduction of the partials over distributed shared memory
-    for (int o = tid; o < N6 * N6 + N6; o += BA_SOLVE_THREADS) {
-      if (o < N6 * N6) {
-        const int row = o / N6, col = o - row * N6;
-        if (row <= col) {
-          float s = sm.S[row][col];
-          for (int r = 1; r < BA_CLUSTER; ++r) {
-            const SolveSmem* peer = cluster.map_shared_rank(&sm, r);
-            s += peer->S[row][col];
-          }
-          sm.S[row][col] = s;
-        }
-      } else {
-        const int row = o - N6 * N6;
-        float s = sm.y[row];
-        for (int r = 1; r < BA_CLUSTER; ++r) {
-          const SolveSmem* peer = cluster.map_shared_rank(&sm, r);
-          s += peer->y[row];
-        }
-        sm.y[row] = s;
-      }
+    // ---- 2. fixed-order reduction over distributed shared memory; mirror into the lower triangle
+    for (int o = tid; o < (N6 + 1) * N6; o += BA_SOLVE_THREADS) {
+      const int row = o / N6, col = o - row * N6;
+      if (row < N6 && row > col) continue;
+      float s = sm.S[row][col];
+      for (int r = 1; r < BA_CLUSTER; ++r) s += cluster.map_shared_rank(&sm, r)->S[row][col];
+      if (row == col) s += 1e-4f * s + 1.0f;            // S += I * (1e-4 * S + 1)   ba_cuda.cu:560
+      sm.S[row][col] = s;
+      if (row < N6) sm.S[col][row] = s;
     }
   }
   cluster.sync();   // peers may now reuse their shared memory
 
   if (N > 0 && rank == 0) {
-    // ---- 3. assemble  S = B - E Q E^T,  y = v - E Q u  from the pair records
-    const int Gp = *a.p_n;
-    // frame span of the pair keys (pairs are sorted by (i, j): i range from the ends, j by a scan)
-    __shared__ long long fr[2];
-    if (tid == 0) { fr[0] = a.p_key_i[0]; fr[1] = a.p_key_i[Gp - 1]; }
-    __syncthreads();
-    {
-      long long jmn = 0x7fffffffffffffffLL, jmx = -0x7fffffffffffffffLL - 1;
-      for (int p = tid; p < Gp; p += BA_SOLVE_THREADS) { const long long j = a.p_key_j[p]; jmn = min(jmn, j); jmx = max(jmx, j); }
-      for (int o = 16; o > 0; o >>= 1) {
-        jmn = min(jmn, __shfl_xor_sync(0xffffffffu, jmn, o));
-        jmx = max(jmx, __shfl_xor_sync(0xffffffffu, jmx, o));
-      }
-      if ((tid & 31) == 0) { atomicMin(&fr[0], jmn); atomicMax(&fr[1], jmx); }
-    }
-    __syncthreads();
-    const long long fmin = fr[0], fmax = fr[1];
-    const long long span = fmax - fmin + 1;
-    const bool use_lut = span <= BA_MAX_FRAMES;
-    const int NF = use_lut ? (int)span : 0;
-    for (int i = tid; i < NF * NF; i += BA_SOLVE_THREADS) sm.lut[i] = 0;
-    __syncthreads();
-    if (use_lut)
-      for (int p = tid; p < Gp; p += BA_SOLVE_THREADS)
-        sm.lut[(int)(a.p_key_i[p] - fmin) * NF + (int)(a.p_key_j[p] - fmin)] = p + 1;
-    __syncthreads();
-    const int foff = (int)(a.t0 - fmin);   // frame index of free pose 0 inside the lut (may be < 0)
-    for (int o = tid; o < N6 * N6 + N6; o += BA_SOLVE_THREADS) {
-      if (o < N6 * N6) {
-        const int row = o / N6, col = o - row * N6;
-        if (row > col) continue;
-        const int bi = row / 6, x = row - 6 * bi, bj = col / 6, yy = col - 6 * bj;
-        float b = 0.0f;
-        if (use_lut) {
-          const int fi = bi + foff, fj = bj + foff;
-          if (bi != bj) {
-            if (fi >= 0 && fi < NF && fj >= 0 && fj < NF) {
-              const int p1 = sm.lut[fi * NF + fj], p2 = sm.lut[fj * NF + fi];
-              if (p1) b += a.rec[(int64_t)(p1 - 1) * BA_REC + 21 + x * 6 + yy];
-              if (p2) b += a.rec[(int64_t)(p2 - 1) * BA_REC + 21 + yy * 6 + x];
-            }
-          } else if (fi >= 0 && fi < NF) {
-            const int t = tri_index(x, yy);
-            for (int f = 0; f < NF; ++f) {
-              const int p1 = sm.lut[fi * NF + f];     // edges leaving frame fi: Ji Ji^T
-              if (p1) {
-                b += a.rec[(int64_t)(p1 - 1) * BA_REC + t];
-                if (f == fi) b += a.rec[(int64_t)(p1 - 1) * BA_REC + 21 + x * 6 + yy] +
-                                  a.rec[(int64_t)(p1 - 1) * BA_REC + 21 + yy * 6 + x];
-              }
-              const int p2 = sm.lut[f * NF + fi];     // edges arriving in frame fi: Jj Jj^T
-              if (p2) b += a.rec[(int64_t)(p2 - 1) * BA_REC + 57 + t];
-            }
-          }
-        } else {
-          // wide frame span (long-range edges): scan the pair list, still in a fixed order
-          const long long Fi = a.t0 + bi, Fj = a.t0 + bj;
-          const int t = tri_index(x, yy);
-          for (int p = 0; p < Gp; ++p) {
-            const long long pi = a.p_key_i[p], pj = a.p_key_j[p];
-            const float* rp = a.rec + (int64_t)p * BA_REC;
-            if (bi != bj) {
-              if (pi == Fi && pj == Fj) b += rp[21 + x * 6 + yy];
-              if (pi == Fj && pj == Fi) b += rp[21 + yy * 6 + x];
-            } else {
-              if (pi == Fi) { b += rp[t]; if (pj == Fi) b += rp[21 + x * 6 + yy] + rp[21 + yy * 6 + x]; }
-              if (pj == Fi) b += rp[57 + t];
-            }
+    // ---- 3. blocked Cholesky of [S; y^T] (lower storage, row N6 = rhs): 6-column panels
+    for (int kb = 0; kb < N; ++kb) {
+      const int k0 = 6 * kb;
+      if (tid == 0) {                                    // factor the 6x6 diagonal block
+        for (int c = 0; c < 6; ++c) {
+          float d = sm.S[k0 + c][k0 + c];
+          for (int l = 0; l < c; ++l) d -= sm.S[k0 + c][k0 + l] * sm.S[k0 + c][k0 + l];
+          d = sqrtf(d);
+          sm.S[k0 + c][k0 + c] = d;
+          for (int r = c + 1; r < 6; ++r) {
+            float v = sm.S[k0 + r][k0 + c];
+            for (int l = 0; l < c; ++l) v -= sm.S[k0 + r][k0 + l] * sm.S[k0 + c][k0 + l];
+            sm.S[k0 + r][k0 + c] = v / d;
           }
         }
-        float s = b - sm.S[row][col];
-        if (row == col) s += 1e-4f * s + 1.0f;      // S += I * (1e-4 * S + 1)   ba_cuda.cu:560
-        sm.S[row][col] = s;
-        sm.S[col][row] = s;
-      } else {
-        const int row = o - N6 * N6;
-        const int bi = row / 6, x = row - 6 * bi;
-        float v = 0.0f;
-        if (use_lut) {
-          const int fi = bi + foff;
-          if (fi >= 0 && fi < NF) {
-            for (int f = 0; f < NF; ++f) {
-              const int p1 = sm.lut[fi * NF + f];
-              if (p1) v += a.rec[(int64_t)(p1 - 1) * BA_REC + 78 + x];
-              const int p2 = sm.lut[f * NF + fi];
-              if (p2) v += a.rec[(int64_t)(p2 - 1) * BA_REC + 84 + x];
-            }
-          }
-        } else {
-          const long long Fi = a.t0 + bi;
-          for (int p = 0; p < Gp; ++p) {
-            if (a.p_key_i[p] == Fi) v += a.rec[(int64_t)p * BA_REC + 78 + x];
-            if (a.p_key_j[p] == Fi) v += a.rec[(int64_t)p * BA_REC + 84 + x];
-          }
+      }
+      __syncthreads();
+      for (int i = k0 + 6 + tid; i <= N6; i += BA_SOLVE_THREADS) {     // panel: rows below (+ rhs row)
+        float v[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          float t = sm.S[i][k0 + c];
+#pragma unroll
+          for (int l = 0; l < 6; ++l) if (l < c) t -= v[l] * sm.S[k0 + c][k0 + l];
+          v[c] = t / sm.S[k0 + c][k0 + c];
         }
-        sm.y[row] = v - sm.y[row];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sm.S[i][k0 + c] = v[c];
       }
-    }
-    __syncthreads();
-
-    // ---- 4. Cholesky S = L L^T in place (lower triangle), column by column
-    for (int k = 0; k < N6; ++k) {
-      if (tid == 0) sm.S[k][k] = sqrtf(sm.S[k][k]);
       __syncthreads();
-      const float dk = sm.S[k][k];
-      for (int i = k + 1 + tid; i < N6; i += BA_SOLVE_THREADS) sm.S[i][k] /= dk;
-      __syncthreads();
-      const int rem = N6 - k - 1;
-      for (int o = tid; o < rem * rem; o += BA_SOLVE_THREADS) {
-        const int i = k + 1 + o / rem, j = k + 1 + o % rem;
-        if (j <= i) sm.S[i][j] -= sm.S[i][k] * sm.S[j][k];
+      const int rem = N6 - k0 - 6;                                      // trailing rows (without rhs)
+      for (int o = tid; o < (rem + 1) * rem; o += BA_SOLVE_THREADS) {
+        const int i = k0 + 6 + o / rem, j = k0 + 6 + o % rem;          // i may be the rhs row N6
+        if (j <= i) {
+          float t = 0.0f;
+#pragma unroll
+          for (int l = 0; l < 6; ++l) t += sm.S[i][k0 + l] * sm.S[j][k0 + l];
+          sm.S[i][j] -= t;
+        }
       }
       __syncthreads();
     }
-    // ---- 5. solve L z = y, L^T x = z with one warp (rows lane, lane+32, ...)
+    // row N6 now holds z = L^-1 y; back substitution L^T x = z with one warp
     if (tid < 32) {
-      for (int k = 0; k < N6; ++k) {
-        float zk = 0.0f;
-        if (tid == (k & 31)) { zk = sm.y[k] / sm.S[k][k]; sm.y[k] = zk; }
-        zk = __shfl_sync(0xffffffffu, zk, k & 31);
-        for (int i = tid; i < N6; i += 32) if (i > k) sm.y[i] -= sm.S[i][k] * zk;
-        __syncwarp();
-      }
       for (int k = N6 - 1; k >= 0; --k) {
         float xk = 0.0f;
-        if (tid == (k & 31)) { xk = sm.y[k] / sm.S[k][k]; sm.dx[k] = xk; }
+        if (tid == (k & 31)) { xk = sm.S[N6][k] / sm.S[k][k]; sm.dx[k] = xk; }
         xk = __shfl_sync(0xffffffffu, xk, k & 31);
-        for (int i = tid; i < N6; i += 32) if (i < k) sm.y[i] -= sm.S[k][i] * xk;
+        for (int i = tid; i < k; i += 32) sm.S[N6][i] -= sm.S[k][i] * xk;
         __syncwarp();
       }
     }
@@ -533,30 +508,30 @@ ba_solve_kernel(const BaArgs a) {
   }
   cluster.sync();
 
-  // ---- 6. depth back-substitution dZ = Q (u - E^T dX) and patch retraction (ba_cuda.cu:209-229)
-  const float* dxs = nullptr;
+  // ---- 4. depth back-substitution dZ = Q (u - E^T dX) and patch retraction (ba_cuda.cu:209-229)
+  float* dxs = sm.Qt;      // reuse: per-CTA copy of dX needs N6 <= 192 floats -> use the Et area instead
+  dxs = &sm.Et[0][0];
   if (N > 0) {
     const SolveSmem* root = cluster.map_shared_rank(&sm, 0);
-    for (int i = tid; i < N6; i += BA_SOLVE_THREADS) sm.y[i] = root->dx[i];
-    dxs = sm.y;
+    for (int i = tid; i < N6; i += BA_SOLVE_THREADS) dxs[i] = root->dx[i];
   }
   __syncthreads();
-  for (int g = m0 + tid; g < m1; g += BA_SOLVE_THREADS) {
-    float s = a.uk[g];
+  for (int g = m0 + warp; g < m1; g += BA_SOLVE_THREADS / 32) {
+    float dot = 0.0f;
     if (N > 0) {
       const float* er = a.Ed + (int64_t)g * N6;
-      float dot = 0.0f;
-      for (int k = 0; k < N6; ++k) dot += er[k] * dxs[k];
-      s -= dot;
+      for (int k = lane; k < N6; k += 32) dot += er[k] * dxs[k];
+      dot = warp_sum(dot);
     }
-    const float dz = a.Qk[g] * s;
+    const float dz = a.Qk[g] * (a.uk[g] - dot);
     float* pd = a.patches + (a.k_key[g] * 3 + 2) * P * P;
     float d = pd[0] + dz;
     d = (d > 20.0f) ? 1.0f : d;
     d = fmaxf(d, 1e-4f);
-    for (int i = 0; i < P * P; ++i) pd[i] = d;
+    __syncwarp();
+    if (lane < P * P) pd[lane] = d;
   }
-  // ---- 7. pose retraction (ba_cuda.cu:178-206), after every CTA is done reading dx
+  // ---- 5. pose retraction (ba_cuda.cu:178-206), after every CTA is done reading dx
   cluster.sync();
   if (N > 0 && rank == 0 && tid < N) {
     float* pp = a.poses + (int64_t)(a.t0 + tid) * 7;

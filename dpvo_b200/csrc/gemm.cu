@@ -16,6 +16,7 @@
 //                           (net.py:84-85 `net[:, ix]` with mask) so the gather never touches HBM twice
 // The weights (<= 0.7 MB per layer) stay L2 resident; X is read once per 192-column half.
 #include "common.cuh"
+#include <cuda.h>          // CUtensorMap types only; the encoder is fetched from the driver at run time
 
 namespace dpvo {
 
@@ -23,12 +24,14 @@ constexpr int GM_M = 128;            // rows per tile == TMEM lanes
 constexpr int GM_N = 192;            // columns per tile (UMMA N, multiple of 16)
 constexpr int GM_K = 64;             // halves per k-block: 128 bytes, one swizzle atom
 constexpr int GM_UK = 16;            // UMMA K for 16-bit operands
-constexpr int GM_STAGES = 5;
-constexpr int GM_LOOK = 4;           // cp.async groups kept in flight per producer thread (< GM_STAGES)
+constexpr int GM_STAGES = 4;
+constexpr int GM_LOOK = 3;           // cp.async groups in flight per producer thread (gather mode, < GM_STAGES)
 constexpr int GM_EPI_THREADS = 128, GM_PROD_THREADS = 128;
 constexpr int GM_THREADS = GM_EPI_THREADS + 32 + GM_PROD_THREADS;
 constexpr int GM_A_BYTES = GM_M * 128, GM_B_BYTES = GM_N * 128;
 constexpr int GM_TMEM_COLS = 512;
+constexpr int GM_EC = 64;            // epilogue column chunk
+constexpr int GM_EP = GM_EC + 2;     // staging pitch in floats (even: float2 aligned)
 
 struct GemmArgs {
   const __half* X; int64_t ldx;
@@ -51,6 +54,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n.reg .pred p;\nWAIT_%=:\n"
@@ -63,6 +69,12 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// 2-D TMA tile load, completion signalled on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -75,11 +87,14 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
@@ -96,7 +111,6 @@ constexpr uint32_t GM_IDESC = (1u << 4) | ((uint32_t)(GM_N >> 3) << 17) | ((uint
 struct GemmBars {
   uint64_t full[GM_STAGES], empty[GM_STAGES], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
-  float bias[4][GM_N];          // per epilogue warp: bias of the current column tile
 };
 
 __device__ __forceinline__ float epi_act(float v, int epi) {
@@ -105,13 +119,17 @@ __device__ __forceinline__ float epi_act(float v, int epi) {
   return v;
 }
 
+// GATHER = false: X and W tiles arrive by TMA (one elected thread, hardware swizzle, OOB rows zero).
+// GATHER = true : X rows are fetched through an index with cp.async by 128 producer threads (W too).
+template <bool GATHER>
 __global__ void __launch_bounds__(GM_THREADS, 1)
-linear_f16_kernel(const GemmArgs a) {
+linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
   extern __shared__ unsigned char gm_smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)gm_smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = base;
   unsigned char* sB = base + GM_STAGES * GM_A_BYTES;
-  GemmBars* bars = reinterpret_cast<GemmBars*>(base + GM_STAGES * (GM_A_BYTES + GM_B_BYTES));
+  float* sStage = reinterpret_cast<float*>(base + GM_STAGES * (GM_A_BYTES + GM_B_BYTES));     // [4 warps][32][GM_EP]
+  GemmBars* bars = reinterpret_cast<GemmBars*>(sStage + 4 * 32 * GM_EP);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = (a.N + GM_N - 1) / GM_N;
@@ -120,7 +138,7 @@ linear_f16_kernel(const GemmArgs a) {
   const int KB = a.K / GM_K;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GM_STAGES; ++s) { mbar_init(&bars->full[s], GM_PROD_THREADS); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < GM_STAGES; ++s) { mbar_init(&bars->full[s], GATHER ? GM_PROD_THREADS : 1); mbar_init(&bars->empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], GM_EPI_THREADS); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -135,51 +153,67 @@ linear_f16_kernel(const GemmArgs a) {
 
   if (warp >= 5) {
     // =========================================================================== producers
-    const int pt = threadIdx.x - (GM_EPI_THREADS + 32);
-    uint32_t it = 0;                       // k-block counter over all tiles of this CTA
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t m0 = (tile / n_tiles_n) * GM_M;
-      const int n0 = (int)(tile % n_tiles_n) * GM_N;
-      // per-thread row pointers of the 8 A chunks and 12 B chunks it copies per k-block
-      const __half* arow[8]; uint32_t aoff[8], abytes[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = pt + GM_PROD_THREADS * i, row = c >> 3, ch = c & 7;
-        int64_t src = m0 + row;
-        bool ok = src < a.rows;
-        if (ok && a.gather) { src = a.gather[src]; ok = src >= 0; }
-        arow[i] = a.X + (ok ? src : 0) * a.ldx + ch * 8;
-        abytes[i] = ok ? 16u : 0u;
-        aoff[i] = row * 128 + ((ch ^ (row & 7)) << 4);
-      }
-      const __half* brow[12]; uint32_t boff[12], bbytes[12];
-#pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        const int c = pt + GM_PROD_THREADS * i, row = c >> 3, ch = c & 7;
-        const bool ok = n0 + row < a.N;
-        brow[i] = a.W + (int64_t)(ok ? n0 + row : 0) * a.ldw + ch * 8;
-        bbytes[i] = ok ? 16u : 0u;
-        boff[i] = row * 128 + ((ch ^ (row & 7)) << 4);
-      }
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const uint32_t s = it % GM_STAGES, ph = (it / GM_STAGES) & 1;
-        mbar_wait(&bars->empty[s], ph ^ 1);
-        const uint32_t da = smem_u32(sA + s * GM_A_BYTES), db = smem_u32(sB + s * GM_B_BYTES);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cp_async16(da + aoff[i], arow[i] + kb * GM_K, abytes[i]);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) cp_async16(db + boff[i], brow[i] + kb * GM_K, bbytes[i]);
-        cp_async_commit();
-        if (it >= GM_LOOK) {               // the group issued GM_LOOK k-blocks ago has landed
-          cp_async_wait<GM_LOOK>();
-          fence_proxy_async();
-          mbar_arrive(&bars->full[(it - GM_LOOK) % GM_STAGES]);
+    if constexpr (!GATHER) {
+      if (warp == 5 && lane == 0) {
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+          const int m0 = (int)((tile / n_tiles_n) * GM_M);
+          const int n0 = (int)(tile % n_tiles_n) * GM_N;
+          for (int kb = 0; kb < KB; ++kb, ++it) {
+            const uint32_t s = it % GM_STAGES, ph = (it / GM_STAGES) & 1;
+            mbar_wait(&bars->empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&bars->full[s], GM_A_BYTES + GM_B_BYTES);
+            tma_load_2d(smem_u32(sA + s * GM_A_BYTES), &tmA, kb * GM_K, m0, &bars->full[s]);
+            tma_load_2d(smem_u32(sB + s * GM_B_BYTES), &tmB, kb * GM_K, n0, &bars->full[s]);
+          }
         }
       }
+    } else {
+      const int pt = threadIdx.x - (GM_EPI_THREADS + 32);
+      uint32_t it = 0;                       // k-block counter over all tiles of this CTA
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t m0 = (tile / n_tiles_n) * GM_M;
+        const int n0 = (int)(tile % n_tiles_n) * GM_N;
+        const __half* arow[8]; uint32_t aoff[8], abytes[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = pt + GM_PROD_THREADS * i, row = c >> 3, ch = c & 7;
+          int64_t src = m0 + row;
+          bool ok = src < a.rows;
+          if (ok && a.gather) { src = a.gather[src]; ok = src >= 0; }
+          arow[i] = a.X + (ok ? src : 0) * a.ldx + ch * 8;
+          abytes[i] = ok ? 16u : 0u;
+          aoff[i] = row * 128 + ((ch ^ (row & 7)) << 4);
+        }
+        const __half* brow[12]; uint32_t boff[12], bbytes[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int c = pt + GM_PROD_THREADS * i, row = c >> 3, ch = c & 7;
+          const bool ok = n0 + row < a.N;
+          brow[i] = a.W + (int64_t)(ok ? n0 + row : 0) * a.ldw + ch * 8;
+          bbytes[i] = ok ? 16u : 0u;
+          boff[i] = row * 128 + ((ch ^ (row & 7)) << 4);
+        }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % GM_STAGES, ph = (it / GM_STAGES) & 1;
+          mbar_wait(&bars->empty[s], ph ^ 1);
+          const uint32_t da = smem_u32(sA + s * GM_A_BYTES), db = smem_u32(sB + s * GM_B_BYTES);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cp_async16(da + aoff[i], arow[i] + kb * GM_K, abytes[i]);
+#pragma unroll
+          for (int i = 0; i < 12; ++i) cp_async16(db + boff[i], brow[i] + kb * GM_K, bbytes[i]);
+          cp_async_commit();
+          if (it >= GM_LOOK) {               // the group issued GM_LOOK k-blocks ago has landed
+            cp_async_wait<GM_LOOK>();
+            fence_proxy_async();
+            mbar_arrive(&bars->full[(it - GM_LOOK) % GM_STAGES]);
+          }
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      for (uint32_t j = (it >= GM_LOOK ? it - GM_LOOK : 0); j < it; ++j) mbar_arrive(&bars->full[j % GM_STAGES]);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (uint32_t j = (it >= GM_LOOK ? it - GM_LOOK : 0); j < it; ++j) mbar_arrive(&bars->full[j % GM_STAGES]);
   } else if (warp == 4) {
     // =========================================================================== MMA issuer
     uint32_t it = 0, tcount = 0;
@@ -206,68 +240,58 @@ linear_f16_kernel(const GemmArgs a) {
     }
   } else {
     // =========================================================================== epilogue
+    // TMEM gives each thread one ROW (lane = row); global memory wants lanes along COLUMNS.  Each warp
+    // therefore transposes 32 rows x 64 columns through its private staging tile and then walks the
+    // rows with lane <-> 2 adjacent columns: every residual / gate load and every store is a fully
+    // coalesced 128- or 256-byte access.
     uint32_t tcount = 0;
-    const int row_in_tile = warp * 32 + lane;
+    float* stg = sStage + warp * 32 * GM_EP;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      const int64_t row = (tile / n_tiles_n) * GM_M + row_in_tile;
+      const int64_t row0 = (tile / n_tiles_n) * GM_M + warp * 32;
       const int n0 = (int)(tile % n_tiles_n) * GM_N;
-      // bias of this column tile -> shared (per warp, so only a warp-level sync is needed)
-      float* sbias = bars->bias[warp];
-      for (int j = lane; j < GM_N; j += 32) sbias[j] = (a.bias && n0 + j < a.N) ? a.bias[n0 + j] : 0.f;
-      __syncwarp();
       mbar_wait(&bars->tmem_full[acc], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * GM_N;
-      const bool row_ok = row < a.rows;
+      const int nrows = (int)min((int64_t)32, a.rows - row0);
 #pragma unroll 1
-      for (int c0 = 0; c0 < GM_N; c0 += 16) {
-        uint32_t r[16];
-        tc_ld16(taddr + c0, r);
-        tc_ld_wait();
-        const int col = n0 + c0;
-        if (row_ok && col < a.N) {
-          float v[16];
+      for (int c0 = 0; c0 < GM_N; c0 += GM_EC) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + sbias[c0 + j];
-          if (a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES) {
+        for (int h = 0; h < GM_EC; h += 32) {
+          uint32_t r[32];
+          tc_ld32(taddr + c0 + h, r);
+          tc_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float g = 1.f;
-              if (a.epilogue == DPVO_EPI_GATEDRES) g = __half2float(a.gate[row * a.ldgate + col + j]);
-              const float rv = (a.res_dtype == DPVO_F32) ? reinterpret_cast<const float*>(a.res)[row * a.ldres + col + j]
-                                                         : __half2float(reinterpret_cast<const __half*>(a.res)[row * a.ldres + col + j]);
-              v[j] = rv + g * v[j];
+          for (int j = 0; j < 32; ++j) stg[lane * GM_EP + h + j] = __uint_as_float(r[j]);
+        }
+        __syncwarp();
+        const int col = n0 + c0 + 2 * lane;
+        if (col < a.N) {
+          float2 bv = make_float2(0.f, 0.f);
+          if (a.bias) bv = *reinterpret_cast<const float2*>(a.bias + col);
+          for (int rr = 0; rr < nrows; ++rr) {
+            const int64_t row = row0 + rr;
+            float2 v = *reinterpret_cast<const float2*>(&stg[rr * GM_EP + 2 * lane]);
+            v.x += bv.x; v.y += bv.y;
+            if (a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES) {
+              float2 g = make_float2(1.f, 1.f);
+              if (a.epilogue == DPVO_EPI_GATEDRES) g = __half22float2(*reinterpret_cast<const __half2*>(a.gate + row * a.ldgate + col));
+              float2 rv;
+              if (a.res_dtype == DPVO_F32) rv = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a.res) + row * a.ldres + col);
+              else rv = __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(a.res) + row * a.ldres + col));
+              v.x = rv.x + g.x * v.x; v.y = rv.y + g.y * v.y;
+            } else {
+              v.x = epi_act(v.x, a.epilogue); v.y = epi_act(v.y, a.epilogue);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = epi_act(v[j], a.epilogue);
-          }
-          if (a.y_dtype == DPVO_F16) {
-            uint4 o[2];
-            __half2* h = reinterpret_cast<__half2*>(o);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.Y) + row * a.ldy + col);
-            dst[0] = o[0]; dst[1] = o[1];
-          } else {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + row * a.ldy + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (a.Y16) {
-            uint4 o[2];
-            __half2* h = reinterpret_cast<__half2*>(o);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            uint4* dst = reinterpret_cast<uint4*>(a.Y16 + row * a.ldy16 + col);
-            dst[0] = o[0]; dst[1] = o[1];
+            if (a.y_dtype == DPVO_F16) *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(a.Y) + row * a.ldy + col) = __floats2half2_rn(v.x, v.y);
+            else *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.Y) + row * a.ldy + col) = v;
+            if (a.Y16) *reinterpret_cast<__half2*>(a.Y16 + row * a.ldy16 + col) = __floats2half2_rn(v.x, v.y);
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[acc]);
-      __syncwarp();
     }
   }
 
@@ -283,17 +307,58 @@ linear_f16_kernel(const GemmArgs a) {
 
 using namespace dpvo;
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major fp16 [rows, cols] with row stride ld (elements) -> tiles of box_rows x 64 columns, 128-byte swizzle
+static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) { set_error("linear_f16: cuTensorMapEncodeTiled is not available from the driver"); return DPVO_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GM_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("linear_f16: cuTensorMapEncodeTiled failed (%d)", (int)r); return DPVO_ERR_CUDA; }
+  return DPVO_OK;
+}
+
 static int linear_launch(const GemmArgs& a, cudaStream_t st) {
-  const size_t smem = GM_STAGES * (GM_A_BYTES + GM_B_BYTES) + sizeof(GemmBars) + 1024;
+  const size_t smem = GM_STAGES * (GM_A_BYTES + GM_B_BYTES) + 4 * 32 * GM_EP * sizeof(float) + sizeof(GemmBars) + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(linear_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(linear_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "linear_f16: cudaFuncSetAttribute");
     attr = true;
   }
   const int64_t tiles = ((a.rows + GM_M - 1) / GM_M) * ((a.N + GM_N - 1) / GM_N);
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
-  linear_f16_kernel<<<grid, GM_THREADS, smem, st>>>(a);
+  CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
+  if (a.gather) {
+    linear_f16_kernel<true><<<grid, GM_THREADS, smem, st>>>(tmA, tmB, a);
+  } else {
+    int rc = make_tmap(&tmA, a.X, a.rows, a.K, a.ldx, GM_M);
+    if (rc) return rc;
+    rc = make_tmap(&tmB, a.W, a.N, a.K, a.ldw, GM_N);
+    if (rc) return rc;
+    linear_f16_kernel<false><<<grid, GM_THREADS, smem, st>>>(tmA, tmB, a);
+  }
   DPVO_LAUNCH_CHECK("linear_f16_kernel");
   return DPVO_OK;
 }
@@ -308,6 +373,7 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
   DPVO_REQUIRE(X && W && Y, "linear_f16: null pointer");
   DPVO_REQUIRE(K % GM_K == 0, "linear_f16: K=%d must be a multiple of %d (pad the operands)", K, GM_K);
   DPVO_REQUIRE(N % 16 == 0, "linear_f16: N=%d must be a multiple of 16", N);
+  DPVO_REQUIRE(rows < (1ll << 31), "linear_f16: too many rows");
   DPVO_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)W & 15) == 0,
                "linear_f16: X / W rows must be 16-byte aligned");
   DPVO_REQUIRE(y_dtype == DPVO_F16 || y_dtype == DPVO_F32, "linear_f16: y dtype");
@@ -315,7 +381,8 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
   DPVO_REQUIRE(epilogue >= DPVO_EPI_NONE && epilogue <= DPVO_EPI_GATEDRES, "linear_f16: unknown epilogue %d", epilogue);
   if (epilogue == DPVO_EPI_RESADD || epilogue == DPVO_EPI_GATEDRES)
     DPVO_REQUIRE(res && (res_dtype == DPVO_F16 || res_dtype == DPVO_F32), "linear_f16: residual operand missing");
-  if (epilogue == DPVO_EPI_GATEDRES) DPVO_REQUIRE(gate, "linear_f16: gate operand missing");
+  if (epilogue == DPVO_EPI_GATEDRES) DPVO_REQUIRE(gate && ldgate % 2 == 0, "linear_f16: gate operand missing or odd stride");
+  DPVO_REQUIRE(!res || ldres % 2 == 0, "linear_f16: residual row stride must be even");
   GemmArgs a;
   a.X = (const __half*)X; a.ldx = ldx; a.W = (const __half*)W; a.ldw = ldw; a.bias = bias; a.gather = gather;
   a.res = res; a.res_dtype = res_dtype; a.ldres = ldres; a.gate = (const __half*)gate; a.ldgate = ldgate;
