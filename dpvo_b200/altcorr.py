@@ -48,11 +48,11 @@ def corr(fmap1, fmap2, coords, ii, jj, radius=1, dropout=1):
     return CorrFn.apply(fmap1, fmap2, coords, ii, jj, radius, dropout)
 
 
-def corr_pyramid(fmap1, pyramid, coords, ii, jj, radius=3, lvl1_div=4.0, pad_to=0):
+def corr_pyramid(fmap1, pyramid, coords, ii, jj, radius=3, lvl1_div=4.0, pad_to=0, out=None):
     """DPVO.corr (dpvo.py:200-207) in one launch: pyramid = (level0, level1); returns [B, M, 882]
     for radius 3, P 3 (feature order x-off, y-off, pi, pj, level).  pad_to=896 returns rows padded
     with zeros to the k-block of the first dense layer of the update operator.  Inference only."""
-    out = extensions()[3].corr_pyramid2(fmap1, pyramid[0], pyramid[1], coords, ii, jj, radius, lvl1_div, pad_to)
+    out = extensions()[3].corr_pyramid2(fmap1, pyramid[0], pyramid[1], coords, ii, jj, radius, lvl1_div, pad_to, out)
     return out.view(out.shape[0], out.shape[1], -1)
 
 

@@ -44,6 +44,7 @@ struct GemmArgs {
   __half* Y16;                 // optional fp16 copy of the result (row stride ldy16)
   int64_t ldy16;
   int64_t rows; int N; int K; int epilogue;
+  int epi_style;               // 0: transposed/coalesced walk, 1: one thread per row with 16-byte accesses
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -254,6 +255,74 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * GM_N;
       const int nrows = (int)min((int64_t)32, a.rows - row0);
+      if (a.epi_style == 1) {
+        // one thread per row: 32 columns per step, 16-byte loads / stores, all loads of a step independent
+        const int64_t row = row0 + lane;
+        const bool row_ok = row < a.rows;
+#pragma unroll 1
+        for (int c0 = 0; c0 < GM_N; c0 += 32) {
+          uint32_t r[32];
+          tc_ld32(taddr + c0, r);
+          const int col = n0 + c0;
+          float4 rv[8]; uint4 gv[4];
+          const bool fused = (a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES);
+          if (fused && row_ok && col < a.N) {
+            if (a.res_dtype == DPVO_F32) {
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res) + row * a.ldres + col);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rv[j] = rp[j];
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.res) + row * a.ldres + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 q = rp[j];
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
+                rv[2 * j] = make_float4(f0.x, f0.y, f1.x, f1.y); rv[2 * j + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+              }
+            }
+            if (a.epilogue == DPVO_EPI_GATEDRES) {
+              const uint4* gp = reinterpret_cast<const uint4*>(a.gate + row * a.ldgate + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) gv[j] = gp[j];
+            }
+          }
+          tc_ld_wait();
+          if (row_ok && col < a.N) {
+            float v[32];
+            const float* sb = a.bias ? a.bias + col : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (sb ? __ldg(sb + j) : 0.f);
+            if (fused) {
+              const float* rf = reinterpret_cast<const float*>(rv);
+              const __half* gh = reinterpret_cast<const __half*>(gv);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = rf[j] + ((a.epilogue == DPVO_EPI_GATEDRES) ? __half2float(gh[j]) : 1.f) * v[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = epi_act(v[j], a.epilogue);
+            }
+            uint4 o[4];
+            __half2* hh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            if (a.y_dtype == DPVO_F16) {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.Y) + row * a.ldy + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = o[j];
+            } else {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + row * a.ldy + col);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (a.Y16) {
+              uint4* dst = reinterpret_cast<uint4*>(a.Y16 + row * a.ldy16 + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = o[j];
+            }
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c0 = 0; c0 < GM_N; c0 += GM_EC) {
 #pragma unroll
@@ -389,5 +458,7 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
   DPVO_REQUIRE(!Y16 || (ldy16 % 8 == 0 && ((uintptr_t)Y16 & 15) == 0), "linear_f16: Y16 rows must be 16-byte aligned");
   a.Y16 = (__half*)Y16; a.ldy16 = ldy16;
   a.Y = Y; a.y_dtype = y_dtype; a.ldy = ldy; a.rows = rows; a.N = N; a.K = K; a.epilogue = epilogue;
+  { const char* e = getenv("DPVO_B200_EPI_STYLE"); a.epi_style = e ? atoi(e) : 1; }
+  if (N % 32 != 0) a.epi_style = 0;
   return linear_launch(a, (cudaStream_t)stream);
 }

@@ -265,7 +265,8 @@ Tensor l_jinv(int g, Tensor X, Tensor a) { return lie_binary(dpvo_lie_jinv, g, X
 
 // ------------------------------------------------------------------------- dpvo_b200_ext
 // DPVO.corr (dpvo.py:200-207) in one launch: returns [1, E, 882]-compatible [B,M,O,O,P,P,2]
-Tensor corr_pyramid2(Tensor fmap1, Tensor fmap2_l0, Tensor fmap2_l1, Tensor coords, Tensor ii, Tensor jj, int radius, double div, int64_t pad_to) {
+Tensor corr_pyramid2(Tensor fmap1, Tensor fmap2_l0, Tensor fmap2_l1, Tensor coords, Tensor ii, Tensor jj, int radius, double div, int64_t pad_to,
+                     c10::optional<Tensor> out_buf) {
   need_cuda(fmap1, "fmap1");
   c10::cuda::CUDAGuard guard(fmap1.device());
   coords = f32c(coords); ii = i64c(ii); jj = i64c(jj);
@@ -273,7 +274,14 @@ Tensor corr_pyramid2(Tensor fmap1, Tensor fmap2_l0, Tensor fmap2_l1, Tensor coor
   const int64_t feat = (int64_t)O * O * P * P * 2;
   const int64_t row = pad_to > feat ? pad_to : feat;
   // padded rows ([B, M, row], zero tail) feed the tcgen05 dense layer directly; unpadded keep the 7-d view
-  Tensor out = (row == feat) ? torch::empty({B, M, O, O, P, P, 2}, fmap1.options()) : torch::zeros({B, M, row}, fmap1.options());
+  // out_buf: a caller-owned [B, M, row] buffer whose padding columns are already zero (reused every update)
+  Tensor out;
+  if (out_buf.has_value()) {
+    out = *out_buf;
+    TORCH_CHECK(out.is_contiguous() && out.scalar_type() == fmap1.scalar_type() && out.numel() == (int64_t)B * M * row, "corr_pyramid2: out buffer must be contiguous [B, M, ", row, "]");
+  } else {
+    out = (row == feat) ? torch::empty({B, M, O, O, P, P, 2}, fmap1.options()) : torch::zeros({B, M, row}, fmap1.options());
+  }
   auto s1 = strides5(fmap1), s20 = strides5(fmap2_l0), s21 = strides5(fmap2_l1);
   check(dpvo_corr_forward_pyramid2(fmap1.data_ptr(), s1.data(), fmap2_l0.data_ptr(), s20.data(), (int)fmap2_l0.size(3),
                                    (int)fmap2_l0.size(4), fmap2_l1.data_ptr(), s21.data(), (int)fmap2_l1.size(3),
@@ -342,7 +350,7 @@ int dt16or32(const Tensor& t) {
 }
 
 std::vector<Tensor> add_layernorm(Tensor a, c10::optional<Tensor> b, c10::optional<Tensor> c, Tensor gamma, Tensor beta,
-                                  double eps, bool relu, bool want32, bool want16) {
+                                  double eps, bool relu, bool want32, bool want16, c10::optional<Tensor> b_index) {
   need_cuda(a, "a");
   c10::cuda::CUDAGuard guard(a.device());
   const int dim = a.size(-1);
@@ -350,14 +358,16 @@ std::vector<Tensor> add_layernorm(Tensor a, c10::optional<Tensor> b, c10::option
   a = a.contiguous();
   Tensor bb, cc;
   int dts[3] = {dt16or32(a), 0, 0};
-  if (b.has_value()) { bb = b->contiguous(); dts[1] = dt16or32(bb); TORCH_CHECK(bb.numel() == a.numel(), "add_layernorm: shape mismatch"); }
+  Tensor bidx;
+  if (b_index.has_value()) { bidx = i64c(*b_index); TORCH_CHECK(bidx.numel() == rows, "add_layernorm: b_index length"); }
+  if (b.has_value()) { bb = b->contiguous(); dts[1] = dt16or32(bb); TORCH_CHECK(bidx.defined() || bb.numel() == a.numel(), "add_layernorm: shape mismatch"); }
   if (c.has_value()) { cc = c->contiguous(); dts[2] = dt16or32(cc); TORCH_CHECK(cc.numel() == a.numel(), "add_layernorm: shape mismatch"); }
   gamma = f32c(gamma); beta = f32c(beta);
   Tensor y32, y16;
   if (want32) y32 = torch::empty(a.sizes(), a.options().dtype(at::kFloat));
   if (want16) y16 = torch::empty(a.sizes(), a.options().dtype(at::kHalf));
   check(dpvo_add_layernorm(a.data_ptr(), bb.defined() ? bb.data_ptr() : nullptr, cc.defined() ? cc.data_ptr() : nullptr, dts,
-                           gamma.data_ptr<float>(), beta.data_ptr<float>(), (float)eps, want32 ? y32.data_ptr() : nullptr,
+                           bidx.defined() ? bidx.data_ptr<int64_t>() : nullptr, gamma.data_ptr<float>(), beta.data_ptr<float>(), (float)eps, want32 ? y32.data_ptr() : nullptr,
                            want16 ? y16.data_ptr() : nullptr, relu ? 1 : 0, rows, dim, stream()),
         "dpvo_b200_ext.add_layernorm");
   return {y32, y16};
@@ -465,7 +475,7 @@ std::vector<Tensor> neighbors_from_groups(Tensor order, Tensor group_of) {
   return {ix, jx};
 }
 
-std::vector<Tensor> update_heads(Tensor net32, Tensor W4, Tensor b4) {
+std::vector<Tensor> update_heads(Tensor net32, Tensor W4, Tensor b4, c10::optional<Tensor> coords) {
   need_cuda(net32, "net");
   c10::cuda::CUDAGuard guard(net32.device());
   TORCH_CHECK(net32.scalar_type() == at::kFloat, "update_heads: net must be float32");
@@ -474,7 +484,10 @@ std::vector<Tensor> update_heads(Tensor net32, Tensor W4, Tensor b4) {
   const int64_t rows = net32.numel() / dim;
   TORCH_CHECK(W4.numel() == 4 * dim && b4.numel() == 4, "update_heads: W4 [4,dim], b4 [4]");
   Tensor delta = torch::empty({1, rows, 2}, net32.options()), weight = torch::empty({1, rows, 2}, net32.options());
-  check(dpvo_update_heads(net32.data_ptr(), W4.data_ptr<float>(), b4.data_ptr<float>(), delta.data_ptr<float>(),
+  Tensor cd; int P = 1;
+  if (coords.has_value()) { cd = f32c(*coords); P = cd.size(-1); TORCH_CHECK(cd.numel() == rows * 2 * P * P, "update_heads: coords must be [rows,2,P,P]"); }
+  check(dpvo_update_heads(net32.data_ptr(), W4.data_ptr<float>(), b4.data_ptr<float>(), cd.defined() ? cd.data_ptr<float>() : nullptr, P,
+                          delta.data_ptr<float>(),
                           weight.data_ptr<float>(), rows, dim, stream()),
         "dpvo_b200_ext.update_heads");
   return {delta, weight};
@@ -523,17 +536,19 @@ PYBIND11_MODULE(lietorch_backends, m) {
 
 PYBIND11_MODULE(dpvo_b200_ext, m) {
   m.def("corr_pyramid2", &corr_pyramid2, "two-level fused correlation", py::arg("fmap1"), py::arg("fmap2_l0"), py::arg("fmap2_l1"),
-        py::arg("coords"), py::arg("ii"), py::arg("jj"), py::arg("radius"), py::arg("div"), py::arg("pad_to") = 0);
+        py::arg("coords"), py::arg("ii"), py::arg("jj"), py::arg("radius"), py::arg("div"), py::arg("pad_to") = 0, py::arg("out") = py::none());
   m.def("group_edges", &group_edges, "device edge grouping", py::arg("key_a"), py::arg("key_b") = py::none(),
         py::arg("sec") = py::none());
   m.def("ba_forward_grouped", &ba_forward_grouped, "fastba.BA on prebuilt edge groupings");
   m.def("reproject_clamped", &reproject_clamped, "pops.transform-compatible fused reprojection");
-  m.def("add_layernorm", &add_layernorm, "fused add + LayerNorm (+ReLU)");
+  m.def("add_layernorm", &add_layernorm, "fused add + LayerNorm (+ReLU)", py::arg("a"), py::arg("b"), py::arg("c"), py::arg("gamma"),
+        py::arg("beta"), py::arg("eps"), py::arg("relu"), py::arg("want32"), py::arg("want16"), py::arg("b_index") = py::none());
   m.def("gather_rows_masked", &gather_rows_masked, "masked row gather");
   m.def("residual_add_", &residual_add_, "in-place residual add with optional row indirection");
   m.def("gated_residual", &gated_residual, "x + sigmoid(g) * r");
   m.def("softagg_reduce", &softagg_reduce, "segment softmax-weighted sum");
-  m.def("update_heads", &update_heads, "delta / weight heads");
+  m.def("update_heads", &update_heads, "delta / weight heads (optionally emitting the BA target)", py::arg("net32"), py::arg("W4"),
+        py::arg("b4"), py::arg("coords") = py::none());
   m.def("linear_f16", &linear_f16, "tcgen05 dense layer", py::arg("x"), py::arg("w"), py::arg("bias") = py::none(),
         py::arg("epilogue") = 0, py::arg("res") = py::none(), py::arg("gate") = py::none(), py::arg("gather") = py::none(),
         py::arg("out_f32") = false, py::arg("out") = py::none(), py::arg("out16") = py::none());

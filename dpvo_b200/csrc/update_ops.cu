@@ -39,6 +39,7 @@ constexpr int MAX_V4 = 8;     // up to 8 float4 per lane -> dim <= 1024
 // ---- add + LayerNorm ------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 add_layernorm_kernel(const void* a, const void* b, const void* c, int da, int db, int dc,
+                     const int64_t* __restrict__ b_index,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      float* y32, __half* y16, int relu, int64_t rows, int dim) {
   const int lane = threadIdx.x & 31;
@@ -46,12 +47,13 @@ add_layernorm_kernel(const void* a, const void* b, const void* c, int da, int db
   for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * ROW_WARPS) {
     float4 v[MAX_V4];
     float s = 0.f;
+    const int64_t rb = b_index ? b_index[r] : r;      // operand b may be gathered (ctx = imap[kk], dpvo.py:334)
 #pragma unroll
     for (int i = 0; i < MAX_V4; ++i) {
       if (i < nv) {
         const int64_t e = r * dim + (i * 32 + lane) * 4;
         float4 t = load4(a, da, e);
-        if (b) t = add4(t, load4(b, db, e));
+        if (b) t = add4(t, load4(b, db, rb * dim + (i * 32 + lane) * 4));
         if (c) t = add4(t, load4(c, dc, e));
         v[i] = t;
         s += (t.x + t.y) + (t.z + t.w);
@@ -161,6 +163,7 @@ softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ g
 // ---- heads: out[r] = (Wd relu(net[r]) + bd, sigmoid(Ww relu(net[r]) + bw)) ---------------------
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 heads_kernel(const float* __restrict__ net, const float* __restrict__ W4, const float* __restrict__ b4,
+             const float* __restrict__ coords, int PP, int centre,
              float* __restrict__ delta, float* __restrict__ weight, int64_t rows, int dim) {
   const int lane = threadIdx.x & 31;
   for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * ROW_WARPS) {
@@ -177,8 +180,13 @@ heads_kernel(const float* __restrict__ net, const float* __restrict__ W4, const 
 #pragma unroll
     for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
     if (lane == 0) {
-      delta[r * 2 + 0] = acc[0] + b4[0];
-      delta[r * 2 + 1] = acc[1] + b4[1];
+      float d0 = acc[0] + b4[0], d1 = acc[1] + b4[1];
+      if (coords) {      // target = reprojected patch centre + delta (dpvo.py:341)
+        d0 += coords[r * 2 * PP + centre];
+        d1 += coords[r * 2 * PP + PP + centre];
+      }
+      delta[r * 2 + 0] = d0;
+      delta[r * 2 + 1] = d1;
       weight[r * 2 + 0] = sigmoidf_(acc[2] + b4[2]);
       weight[r * 2 + 1] = sigmoidf_(acc[3] + b4[3]);
     }
@@ -195,6 +203,7 @@ static inline bool ok_dt(int d) { return d == DPVO_F16 || d == DPVO_F32; }
 using namespace dpvo;
 
 extern "C" int dpvo_add_layernorm(const void* a, const void* b, const void* c, const int* in_dtypes,
+                                  const int64_t* b_index,
                                   const float* gamma, const float* beta, float eps,
                                   void* y32, void* y16, int relu, int64_t rows, int dim, void* stream) {
   DPVO_REQUIRE(rows >= 0 && dim > 0, "add_layernorm: bad sizes");
@@ -203,7 +212,8 @@ extern "C" int dpvo_add_layernorm(const void* a, const void* b, const void* c, c
   DPVO_REQUIRE(dim % 128 == 0 && dim <= 128 * MAX_V4, "add_layernorm: dim must be a multiple of 128, <= %d", 128 * MAX_V4);
   DPVO_REQUIRE(ok_dt(in_dtypes[0]) && (!b || ok_dt(in_dtypes[1])) && (!c || ok_dt(in_dtypes[2])), "add_layernorm: dtype");
   add_layernorm_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      a, b, c, in_dtypes[0], b ? in_dtypes[1] : 0, c ? in_dtypes[2] : 0, gamma, beta, eps, (float*)y32, (__half*)y16, relu, rows, dim);
+      a, b, c, in_dtypes[0], b ? in_dtypes[1] : 0, c ? in_dtypes[2] : 0, b ? b_index : nullptr, gamma, beta, eps, (float*)y32, (__half*)y16,
+      relu, rows, dim);
   DPVO_LAUNCH_CHECK("add_layernorm_kernel");
   return DPVO_OK;
 }
@@ -253,12 +263,13 @@ extern "C" int dpvo_softagg_reduce(const void* f16, const void* g16, int64_t ld,
   return DPVO_OK;
 }
 
-extern "C" int dpvo_update_heads(const void* net32, const float* W4, const float* b4, float* delta, float* weight,
-                                 int64_t rows, int dim, void* stream) {
+extern "C" int dpvo_update_heads(const void* net32, const float* W4, const float* b4, const float* coords, int P,
+                                 float* delta, float* weight, int64_t rows, int dim, void* stream) {
   DPVO_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0, "update_heads: bad sizes");
   if (rows == 0) return DPVO_OK;
   DPVO_REQUIRE(net32 && W4 && b4 && delta && weight, "update_heads: null pointer");
-  heads_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>((const float*)net32, W4, b4, delta, weight, rows, dim);
+  heads_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>((const float*)net32, W4, b4, coords, P * P, (P / 2) * P + P / 2,
+                                                                         delta, weight, rows, dim);
   DPVO_LAUNCH_CHECK("heads_kernel");
   return DPVO_OK;
 }

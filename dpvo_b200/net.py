@@ -119,9 +119,13 @@ class Update(nn.Module):
 
     # ------------------------------------------------------------------------------- forward
     @torch.no_grad()
-    def forward(self, net, inp, corr, flow, ii, jj, kk, groups_kk=None, groups_ij=None):
+    def forward(self, net, inp, corr, flow, ii, jj, kk, groups_kk=None, groups_ij=None, inp_index=None, coords=None):
         """net [1,E,384] (fp16 or fp32), inp [1,E,384], corr [1,E,882 or 896], ii/jj/kk int64 [E].
-        Returns (net fp32, (delta [1,E,2], weight [1,E,2], None)) like net.py:92."""
+        Returns (net fp32, (delta [1,E,2], weight [1,E,2], None)) like net.py:92.
+        Optional fusions for the inference loop: `inp_index` -- `inp` is the whole context table and row
+        e uses inp[inp_index[e]] (dpvo.py:334); `coords` [1,E,2,P,P] -- `delta` is returned as the BA
+        target coords[..., P//2, P//2] + delta (dpvo.py:341)."""
+        self._inp_index, self._coords = inp_index, coords
         corr = corr if corr.dtype == torch.half else corr.half()
         if corr.shape[-1] != CORR_PAD:
             corr = F.pad(corr, (0, CORR_PAD - corr.shape[-1]))
@@ -150,7 +154,7 @@ class Update(nn.Module):
         h = L(L(corr, "corr0", RELU), "corr2")
         _, h = ex.add_layernorm(h, None, None, self.corr[3].weight, self.corr[3].bias, 1e-3, True, False, True)
         h = L(h, "corr5")
-        net32, n16 = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, True)
+        net32, n16 = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, True, self._inp_index)
         ix, jx = ex.neighbors_from_groups(groups_kk.order, groups_kk.group_of)
         for idx, a, b in ((ix, "c1a", "c1b"), (jx, "c2a", "c2b")):
             u = L(n16, a, RELU, gather=idx)                       # c(mask * net[idx]) first layer
@@ -165,7 +169,7 @@ class Update(nn.Module):
             gate = L(x16, "gr%d_g" % i, SIGM)
             r1 = L(x16, "gr%d_a" % i, RELU)
             L(r1, "gr%d_b" % i, GATED, res=x32, gate=gate, out_f32=True, out=x32)
-        delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"])
+        delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"], self._coords)
         return x32, (delta, weight, None)
 
     def _forward_cublas(self, net, inp, corr, groups_kk, groups_ij):
@@ -175,7 +179,7 @@ class Update(nn.Module):
         h = self.dense(h, P["corr2"])
         _, h = ex.add_layernorm(h, None, None, self.corr[3].weight, self.corr[3].bias, 1e-3, True, False, True)
         h = self.dense(h, P["corr5"])
-        net32, _ = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, False)
+        net32, _ = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, False, self._inp_index)
         ix, jx = ex.neighbors_from_groups(groups_kk.order, groups_kk.group_of)
         n16 = None
         for idx, a, b in ((ix, "c1a", "c1b"), (jx, "c2a", "c2b")):
@@ -192,5 +196,5 @@ class Update(nn.Module):
             gate = self.dense(x16, P["gr%d_g" % i])
             r2 = self.dense(self.dense(x16, P["gr%d_a" % i], relu=True), P["gr%d_b" % i])
             x32, _ = ex.gated_residual(x32, gate, r2, False)
-        delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"])
+        delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"], self._coords)
         return x32, (delta, weight, None)

@@ -34,6 +34,7 @@ class UpdateRunner:
         self.patches0 = state.patches.clone()
         self.net = torch.zeros(1, state.E, DIM, device=dev, dtype=torch.float32)
         self.timers = None
+        self.corr_buf = torch.zeros(1, state.E, 896, device=dev, dtype=torch.half)   # padding columns stay zero
         # host-known bounds on the number of groups (no device->host sync in the step)
         n_live_frames = int((state.kk // self.M).unique().numel())
         self.max_patch_groups = n_live_frames * self.M
@@ -56,14 +57,15 @@ class UpdateRunner:
         coords = pops.transform_fused(poses, patches, intr, s.ii, s.jj, s.kk)               # [1,E,2,3,3]
         if ev is not None:
             ev["corr0"].record()
-        corr = altcorr.corr_pyramid(s.gmap, (s.fmap1, s.fmap2), coords, self.kk_ring, self.jj_ring, 3, 4.0, 896)
+        corr = altcorr.corr_pyramid(s.gmap, (s.fmap1, s.fmap2), coords, self.kk_ring, self.jj_ring, 3, 4.0, 896, self.corr_buf)
         if ev is not None:
             ev["corr1"].record()
-        ctx = s.imap[:, self.kk_ring]
         groups_kk = EdgeGroups(s.kk, None, s.jj, max_groups=self.max_patch_groups)
         groups_ij = EdgeGroups(s.ii, s.jj, None, max_groups=self.max_pair_groups)
-        self.net, (delta, weight, _) = self.update(self.net, ctx, corr, None, s.ii, s.jj, s.kk, groups_kk, groups_ij)
-        target = coords[:, :, :, 1, 1] + delta
+        # context gather (dpvo.py:334) and target = centre + delta (dpvo.py:341) are folded into the
+        # first LayerNorm pass and the heads kernel
+        self.net, (target, weight, _) = self.update(self.net, s.imap, corr, None, s.ii, s.jj, s.kk, groups_kk, groups_ij,
+                                                    inp_index=self.kk_ring, coords=coords)
         if ev is not None:
             ev["ba0"].record()
         fastba.BA_grouped(poses, patches, intr, target, weight, self.lmbda, s.ii, s.jj, s.kk, s.t0, s.n,

@@ -276,8 +276,11 @@ int dpvo_lie_jinv(int group, int dtype, const void* X, const void* a, void* b, i
  * (b, c optional, may be NULL).  rows x dim, dim % 128 == 0, dim <= 1024; eps as given (1e-3 in
  * Update: net.py:41,47,49,57).  a/b/c element types in_dtypes[3] (F16/F32); gamma/beta fp32;
  * statistics in fp32.  Result written as fp32 (y32) and/or fp16 (y16) in the same pass.
+ * b_index (optional, int64 [rows]): operand b is read from row b_index[r] -- the context gather
+ * `imap[:, kk % (M*pmem)]` of dpvo.py:334 folded into the pass.
  */
 int dpvo_add_layernorm(const void* a, const void* b, const void* c, const int* in_dtypes,
+                       const int64_t* b_index,
                        const float* gamma, const float* beta, float eps,
                        void* y32, void* y16, int relu, int64_t rows, int dim, void* stream);
 
@@ -310,9 +313,11 @@ int dpvo_softagg_reduce(const void* f16, const void* g16, int64_t ld, const int3
 /*
  * The two output heads (net.py:62-71, 92): delta = Wd relu(net) + bd, weight = sigmoid(Ww relu(net) + bw).
  * W4 fp32 [4, dim] = rows (Wd[0], Wd[1], Ww[0], Ww[1]); b4 fp32 [4]; delta, weight fp32 [rows, 2].
+ * coords (optional, fp32 [rows, 2, P, P]): when given, `delta` receives the BA target
+ * coords[:, :, P/2, P/2] + delta directly (dpvo.py:341).
  */
-int dpvo_update_heads(const void* net32, const float* W4, const float* b4, float* delta, float* weight,
-                      int64_t rows, int dim, void* stream);
+int dpvo_update_heads(const void* net32, const float* W4, const float* b4, const float* coords, int P,
+                      float* delta, float* weight, int64_t rows, int dim, void* stream);
 
 /*
  * Dense layer on tensor cores (tcgen05.mma, fp16 operands, fp32 accumulation in TMEM):
