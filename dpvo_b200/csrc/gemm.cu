@@ -24,14 +24,16 @@ constexpr int GM_M = 128;            // rows per tile == TMEM lanes
 constexpr int GM_N = 192;            // columns per tile (UMMA N, multiple of 16)
 constexpr int GM_K = 64;             // halves per k-block: 128 bytes, one swizzle atom
 constexpr int GM_UK = 16;            // UMMA K for 16-bit operands
-constexpr int GM_STAGES = 4;
-constexpr int GM_LOOK = 3;           // cp.async groups in flight per producer thread (gather mode, < GM_STAGES)
-constexpr int GM_EPI_THREADS = 128, GM_PROD_THREADS = 128;
+constexpr int GM_STAGES = 5;
+constexpr int GM_LOOK = 4;           // cp.async groups in flight per producer thread (gather mode, < GM_STAGES)
+constexpr int GM_EPI_WARPS = 8;      // two warps per TMEM lane quarter, each owning half of the tile's columns
+constexpr int GM_EPI_THREADS = GM_EPI_WARPS * 32, GM_PROD_THREADS = 128;
+constexpr int GM_MMA_WARP = GM_EPI_WARPS;
 constexpr int GM_THREADS = GM_EPI_THREADS + 32 + GM_PROD_THREADS;
 constexpr int GM_A_BYTES = GM_M * 128, GM_B_BYTES = GM_N * 128;
 constexpr int GM_TMEM_COLS = 512;
-constexpr int GM_EC = 64;            // epilogue column chunk
-constexpr int GM_EP = GM_EC + 2;     // staging pitch in floats (even: float2 aligned)
+constexpr int GM_WS_MAXKB = 6;       // weight-stationary mode: K <= 384 (6 k-blocks of the weight slice stay in smem)
+constexpr int GM_WS_ASTAGES = 4;     // activation ring depth in weight-stationary mode
 
 struct GemmArgs {
   const __half* X; int64_t ldx;
@@ -44,7 +46,6 @@ struct GemmArgs {
   __half* Y16;                 // optional fp16 copy of the result (row stride ldy16)
   int64_t ldy16;
   int64_t rows; int N; int K; int epilogue;
-  int epi_style;               // 0: transposed/coalesced walk, 1: one thread per row with 16-byte accesses
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -110,27 +111,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 constexpr uint32_t GM_IDESC = (1u << 4) | ((uint32_t)(GM_N >> 3) << 17) | ((uint32_t)(GM_M >> 4) << 24);
 
 struct GemmBars {
-  uint64_t full[GM_STAGES], empty[GM_STAGES], tmem_full[2], tmem_empty[2];
+  uint64_t full[GM_STAGES], empty[GM_STAGES], tmem_full[2], tmem_empty[2], wfull;
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float epi_act(float v, int epi) {
-  if (epi == DPVO_EPI_RELU) return fmaxf(v, 0.f);
-  if (epi == DPVO_EPI_SIGMOID) return 1.0f / (1.0f + __expf(-v));
-  return v;
-}
-
 // GATHER = false: X and W tiles arrive by TMA (one elected thread, hardware swizzle, OOB rows zero).
 // GATHER = true : X rows are fetched through an index with cp.async by 128 producer threads (W too).
-template <bool GATHER>
+// WS = true (weight stationary, K <= 384): a CTA works on ONE 192-column slice of the layer for its whole
+// life, loads that slice of W once (<= 144 KB, resident) and streams only activation tiles.  Streaming both
+// operands needs (128+192)*128 B per 128x192x64 MACs = 107 B/clk/SM at the tensor-pipe rate, 2.5x what L2
+// delivers per SM; with W resident it is 43 B/clk/SM.
+template <bool GATHER, bool WS, int EPI>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
   extern __shared__ unsigned char gm_smem_raw[];
+  constexpr int NST = WS ? GM_WS_ASTAGES : GM_STAGES;
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)gm_smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = base;
-  unsigned char* sB = base + GM_STAGES * GM_A_BYTES;
-  float* sStage = reinterpret_cast<float*>(base + GM_STAGES * (GM_A_BYTES + GM_B_BYTES));     // [4 warps][32][GM_EP]
-  GemmBars* bars = reinterpret_cast<GemmBars*>(sStage + 4 * 32 * GM_EP);
+  unsigned char* sB = base + NST * GM_A_BYTES;
+  GemmBars* bars = reinterpret_cast<GemmBars*>(sB + (WS ? GM_WS_MAXKB : GM_STAGES) * GM_B_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = (a.N + GM_N - 1) / GM_N;
@@ -140,10 +139,11 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GM_STAGES; ++s) { mbar_init(&bars->full[s], GATHER ? GM_PROD_THREADS : 1); mbar_init(&bars->empty[s], 1); }
+    mbar_init(&bars->wfull, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], GM_EPI_THREADS); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == GM_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&bars->tmem_base)), "n"(GM_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
@@ -152,26 +152,39 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp >= 5) {
+  if (warp > GM_MMA_WARP) {
     // =========================================================================== producers
     if constexpr (!GATHER) {
-      if (warp == 5 && lane == 0) {
+      if (warp == GM_MMA_WARP + 1 && lane == 0) {
         uint32_t it = 0;
+        if constexpr (WS) {                  // the CTA's weight slice, once
+          const int n0 = (int)(blockIdx.x % n_tiles_n) * GM_N;
+          mbar_arrive_expect_tx(&bars->wfull, KB * GM_B_BYTES);
+          for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_u32(sB + kb * GM_B_BYTES), &tmB, kb * GM_K, n0, &bars->wfull);
+        }
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
           const int m0 = (int)((tile / n_tiles_n) * GM_M);
           const int n0 = (int)(tile % n_tiles_n) * GM_N;
           for (int kb = 0; kb < KB; ++kb, ++it) {
-            const uint32_t s = it % GM_STAGES, ph = (it / GM_STAGES) & 1;
+            const uint32_t s = it % NST, ph = (it / NST) & 1;
             mbar_wait(&bars->empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&bars->full[s], GM_A_BYTES + GM_B_BYTES);
+            mbar_arrive_expect_tx(&bars->full[s], WS ? GM_A_BYTES : GM_A_BYTES + GM_B_BYTES);
             tma_load_2d(smem_u32(sA + s * GM_A_BYTES), &tmA, kb * GM_K, m0, &bars->full[s]);
-            tma_load_2d(smem_u32(sB + s * GM_B_BYTES), &tmB, kb * GM_K, n0, &bars->full[s]);
+            if constexpr (!WS) tma_load_2d(smem_u32(sB + s * GM_B_BYTES), &tmB, kb * GM_K, n0, &bars->full[s]);
           }
         }
       }
     } else {
       const int pt = threadIdx.x - (GM_EPI_THREADS + 32);
       uint32_t it = 0;                       // k-block counter over all tiles of this CTA
+      constexpr int LOOK = WS ? GM_WS_ASTAGES - 1 : GM_LOOK;
+      if constexpr (WS) {
+        if (pt == 0) {
+          const int n0 = (int)(blockIdx.x % n_tiles_n) * GM_N;
+          mbar_arrive_expect_tx(&bars->wfull, KB * GM_B_BYTES);
+          for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_u32(sB + kb * GM_B_BYTES), &tmB, kb * GM_K, n0, &bars->wfull);
+        }
+      }
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t m0 = (tile / n_tiles_n) * GM_M;
         const int n0 = (int)(tile % n_tiles_n) * GM_N;
@@ -196,40 +209,44 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           boff[i] = row * 128 + ((ch ^ (row & 7)) << 4);
         }
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          const uint32_t s = it % GM_STAGES, ph = (it / GM_STAGES) & 1;
+          const uint32_t s = it % NST, ph = (it / NST) & 1;
           mbar_wait(&bars->empty[s], ph ^ 1);
-          const uint32_t da = smem_u32(sA + s * GM_A_BYTES), db = smem_u32(sB + s * GM_B_BYTES);
+          const uint32_t da = smem_u32(sA + s * GM_A_BYTES);
 #pragma unroll
           for (int i = 0; i < 8; ++i) cp_async16(da + aoff[i], arow[i] + kb * GM_K, abytes[i]);
+          if constexpr (!WS) {
+            const uint32_t db = smem_u32(sB + s * GM_B_BYTES);
 #pragma unroll
-          for (int i = 0; i < 12; ++i) cp_async16(db + boff[i], brow[i] + kb * GM_K, bbytes[i]);
+            for (int i = 0; i < 12; ++i) cp_async16(db + boff[i], brow[i] + kb * GM_K, bbytes[i]);
+          }
           cp_async_commit();
-          if (it >= GM_LOOK) {               // the group issued GM_LOOK k-blocks ago has landed
-            cp_async_wait<GM_LOOK>();
+          if (it >= LOOK) {                  // the group issued LOOK k-blocks ago has landed
+            cp_async_wait<LOOK>();
             fence_proxy_async();
-            mbar_arrive(&bars->full[(it - GM_LOOK) % GM_STAGES]);
+            mbar_arrive(&bars->full[(it - LOOK) % NST]);
           }
         }
       }
       cp_async_wait<0>();
       fence_proxy_async();
-      for (uint32_t j = (it >= GM_LOOK ? it - GM_LOOK : 0); j < it; ++j) mbar_arrive(&bars->full[j % GM_STAGES]);
+      for (uint32_t j = (it >= LOOK ? it - LOOK : 0); j < it; ++j) mbar_arrive(&bars->full[j % NST]);
     }
-  } else if (warp == 4) {
+  } else if (warp == GM_MMA_WARP) {
     // =========================================================================== MMA issuer
     uint32_t it = 0, tcount = 0;
+    if constexpr (WS) mbar_wait(&bars->wfull, 0);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&bars->tmem_empty[acc], aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * GM_N;
       for (int kb = 0; kb < KB; ++kb, ++it) {
-        const uint32_t s = it % GM_STAGES, ph = (it / GM_STAGES) & 1;
+        const uint32_t s = it % NST, ph = (it / NST) & 1;
         mbar_wait(&bars->full[s], ph);
         tc_fence_after();
         if (lane == 0) {
           const uint64_t ad = umma_desc_sw128(smem_u32(sA + s * GM_A_BYTES));
-          const uint64_t bd = umma_desc_sw128(smem_u32(sB + s * GM_B_BYTES));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sB + (WS ? kb : (int)s) * GM_B_BYTES));
 #pragma unroll
           for (int k = 0; k < GM_K / GM_UK; ++k)
             tc_mma_f16(d_tmem, ad + (uint64_t)(k * GM_UK * 2 / 16), bd + (uint64_t)(k * GM_UK * 2 / 16), GM_IDESC, (kb | k) != 0);
@@ -241,123 +258,96 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // =========================================================================== epilogue
-    // TMEM gives each thread one ROW (lane = row); global memory wants lanes along COLUMNS.  Each warp
-    // therefore transposes 32 rows x 64 columns through its private staging tile and then walks the
-    // rows with lane <-> 2 adjacent columns: every residual / gate load and every store is a fully
-    // coalesced 128- or 256-byte access.
+    // TMEM hands every thread one accumulator ROW (lane = row); a warp may only touch the lane quarter
+    // warp % 4.  Eight warps share a tile: warps q and q+4 own the left / right 96 columns of quarter q.
+    // All element-wise work of the layer runs here, so the epilogue needs the issue slots of two
+    // warps per scheduler to keep up with the tensor pipe (4 warps were 3x slower than the MMAs).
+    // Per step: 32 columns, all loads of the step (bias, residual, gate) issued before the math.
     uint32_t tcount = 0;
-    float* stg = sStage + warp * 32 * GM_EP;
+    const int quarter = warp & 3, half = warp >> 2;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      const int64_t row0 = (tile / n_tiles_n) * GM_M + warp * 32;
-      const int n0 = (int)(tile % n_tiles_n) * GM_N;
+      const int64_t row = (tile / n_tiles_n) * GM_M + quarter * 32 + lane;
+      const int n0 = (int)(tile % n_tiles_n) * GM_N + half * (GM_N / 2);
+      const bool row_ok = row < a.rows;
+      constexpr bool fused = (EPI == DPVO_EPI_RESADD || EPI == DPVO_EPI_GATEDRES);
       mbar_wait(&bars->tmem_full[acc], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * GM_N;
-      const int nrows = (int)min((int64_t)32, a.rows - row0);
-      if (a.epi_style == 1) {
-        // one thread per row: 32 columns per step, 16-byte loads / stores, all loads of a step independent
-        const int64_t row = row0 + lane;
-        const bool row_ok = row < a.rows;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GM_N + half * (GM_N / 2);
 #pragma unroll 1
-        for (int c0 = 0; c0 < GM_N; c0 += 32) {
-          uint32_t r[32];
-          tc_ld32(taddr + c0, r);
-          const int col = n0 + c0;
-          float4 rv[8]; uint4 gv[4];
-          const bool fused = (a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES);
-          if (fused && row_ok && col < a.N) {
-            if (a.res_dtype == DPVO_F32) {
-              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res) + row * a.ldres + col);
+      for (int c0 = 0; c0 < GM_N / 2; c0 += 32) {
+        uint32_t r[32];
+        tc_ld32(taddr + c0, r);
+        const int col = n0 + c0;
+        const bool ok = row_ok && col < a.N;
+        float4 rv[8]; uint4 gv[4];
+        if (fused && ok) {
+          if (a.res_dtype == DPVO_F32) {
+            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res) + row * a.ldres + col);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) rv[j] = rp[j];
-            } else {
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.res) + row * a.ldres + col);
+            for (int j = 0; j < 8; ++j) rv[j] = rp[j];
+          } else {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.res) + row * a.ldres + col);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 q = rp[j];
-                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
-                rv[2 * j] = make_float4(f0.x, f0.y, f1.x, f1.y); rv[2 * j + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
-              }
-            }
-            if (a.epilogue == DPVO_EPI_GATEDRES) {
-              const uint4* gp = reinterpret_cast<const uint4*>(a.gate + row * a.ldgate + col);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) gv[j] = gp[j];
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = rp[j];
+              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+              const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
+              rv[2 * j] = make_float4(f0.x, f0.y, f1.x, f1.y); rv[2 * j + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
             }
           }
-          tc_ld_wait();
-          if (row_ok && col < a.N) {
-            float v[32];
-            const float* sb = a.bias ? a.bias + col : nullptr;
+          if constexpr (EPI == DPVO_EPI_GATEDRES) {
+            const uint4* gp = reinterpret_cast<const uint4*>(a.gate + row * a.ldgate + col);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (sb ? __ldg(sb + j) : 0.f);
-            if (fused) {
-              const float* rf = reinterpret_cast<const float*>(rv);
-              const __half* gh = reinterpret_cast<const __half*>(gv);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = rf[j] + ((a.epilogue == DPVO_EPI_GATEDRES) ? __half2float(gh[j]) : 1.f) * v[j];
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = epi_act(v[j], a.epilogue);
-            }
-            uint4 o[4];
-            __half2* hh = reinterpret_cast<__half2*>(o);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) hh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-            if (a.y_dtype == DPVO_F16) {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.Y) + row * a.ldy + col);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j] = o[j];
-            } else {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + row * a.ldy + col);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (a.Y16) {
-              uint4* dst = reinterpret_cast<uint4*>(a.Y16 + row * a.ldy16 + col);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j] = o[j];
-            }
+            for (int j = 0; j < 4; ++j) gv[j] = gp[j];
           }
         }
-      } else
-#pragma unroll 1
-      for (int c0 = 0; c0 < GM_N; c0 += GM_EC) {
+        float4 bv[8];
+        if (a.bias && col < a.N) {
+          const float4* bp = reinterpret_cast<const float4*>(a.bias + col);      // same address in every lane: broadcast
 #pragma unroll
-        for (int h = 0; h < GM_EC; h += 32) {
-          uint32_t r[32];
-          tc_ld32(taddr + c0 + h, r);
-          tc_ld_wait();
+          for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * GM_EP + h + j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncwarp();
-        const int col = n0 + c0 + 2 * lane;
-        if (col < a.N) {
-          float2 bv = make_float2(0.f, 0.f);
-          if (a.bias) bv = *reinterpret_cast<const float2*>(a.bias + col);
-          for (int rr = 0; rr < nrows; ++rr) {
-            const int64_t row = row0 + rr;
-            float2 v = *reinterpret_cast<const float2*>(&stg[rr * GM_EP + 2 * lane]);
-            v.x += bv.x; v.y += bv.y;
-            if (a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES) {
-              float2 g = make_float2(1.f, 1.f);
-              if (a.epilogue == DPVO_EPI_GATEDRES) g = __half22float2(*reinterpret_cast<const __half2*>(a.gate + row * a.ldgate + col));
-              float2 rv;
-              if (a.res_dtype == DPVO_F32) rv = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a.res) + row * a.ldres + col);
-              else rv = __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(a.res) + row * a.ldres + col));
-              v.x = rv.x + g.x * v.x; v.y = rv.y + g.y * v.y;
-            } else {
-              v.x = epi_act(v.x, a.epilogue); v.y = epi_act(v.y, a.epilogue);
-            }
-            if (a.y_dtype == DPVO_F16) *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(a.Y) + row * a.ldy + col) = __floats2half2_rn(v.x, v.y);
-            else *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.Y) + row * a.ldy + col) = v;
-            if (a.Y16) *reinterpret_cast<__half2*>(a.Y16 + row * a.ldy16 + col) = __floats2half2_rn(v.x, v.y);
+        tc_ld_wait();
+        if (ok) {
+          float v[32];
+          const float* bf = reinterpret_cast<const float*>(bv);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bf[j];
+          if constexpr (fused) {
+            const float* rf = reinterpret_cast<const float*>(rv);
+            const __half* gh = reinterpret_cast<const __half*>(gv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (EPI == DPVO_EPI_GATEDRES) ? rf[j] + __half2float(gh[j]) * v[j] : rf[j] + v[j];
+          } else if constexpr (EPI == DPVO_EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if constexpr (EPI == DPVO_EPI_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+          }
+          uint4 o[4];
+          __half2* hh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+          if (a.y_dtype == DPVO_F16) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.Y) + row * a.ldy + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = o[j];
+          } else {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + row * a.ldy + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (a.Y16) {
+            uint4* dst = reinterpret_cast<uint4*>(a.Y16 + row * a.ldy16 + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = o[j];
           }
         }
-        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[acc]);
@@ -366,7 +356,7 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == GM_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(GM_TMEM_COLS));
   }
@@ -406,30 +396,47 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
   return DPVO_OK;
 }
 
-static int linear_launch(const GemmArgs& a, cudaStream_t st) {
-  const size_t smem = GM_STAGES * (GM_A_BYTES + GM_B_BYTES) + 4 * 32 * GM_EP * sizeof(float) + sizeof(GemmBars) + 1024;
+template <bool GATHER, bool WS, int EPI>
+static int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, unsigned grid, cudaStream_t st) {
+  const size_t smem = (WS ? (size_t)GM_WS_ASTAGES * GM_A_BYTES + (size_t)GM_WS_MAXKB * GM_B_BYTES
+                          : (size_t)GM_STAGES * (GM_A_BYTES + GM_B_BYTES)) + sizeof(GemmBars) + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(linear_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(linear_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(linear_f16_kernel<GATHER, WS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "linear_f16: cudaFuncSetAttribute");
     attr = true;
   }
-  const int64_t tiles = ((a.rows + GM_M - 1) / GM_M) * ((a.N + GM_N - 1) / GM_N);
-  const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
-  CUtensorMap tmA, tmB;
-  memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
-  if (a.gather) {
-    linear_f16_kernel<true><<<grid, GM_THREADS, smem, st>>>(tmA, tmB, a);
-  } else {
-    int rc = make_tmap(&tmA, a.X, a.rows, a.K, a.ldx, GM_M);
-    if (rc) return rc;
-    rc = make_tmap(&tmB, a.W, a.N, a.K, a.ldw, GM_N);
-    if (rc) return rc;
-    linear_f16_kernel<false><<<grid, GM_THREADS, smem, st>>>(tmA, tmB, a);
-  }
+  linear_f16_kernel<GATHER, WS, EPI><<<grid, GM_THREADS, smem, st>>>(tmA, tmB, a);
   DPVO_LAUNCH_CHECK("linear_f16_kernel");
   return DPVO_OK;
+}
+
+template <bool GATHER, bool WS>
+static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, unsigned grid, cudaStream_t st) {
+  switch (a.epilogue) {
+    case DPVO_EPI_NONE: return launch_epi<GATHER, WS, DPVO_EPI_NONE>(tmA, tmB, a, grid, st);
+    case DPVO_EPI_RELU: return launch_epi<GATHER, WS, DPVO_EPI_RELU>(tmA, tmB, a, grid, st);
+    case DPVO_EPI_SIGMOID: return launch_epi<GATHER, WS, DPVO_EPI_SIGMOID>(tmA, tmB, a, grid, st);
+    case DPVO_EPI_RESADD: return launch_epi<GATHER, WS, DPVO_EPI_RESADD>(tmA, tmB, a, grid, st);
+    default: return launch_epi<GATHER, WS, DPVO_EPI_GATEDRES>(tmA, tmB, a, grid, st);
+  }
+}
+
+static int linear_launch(const GemmArgs& a, cudaStream_t st) {
+  const int n_tiles_n = (a.N + GM_N - 1) / GM_N;
+  const int64_t tiles = ((a.rows + GM_M - 1) / GM_M) * n_tiles_n;
+  const bool ws = (a.K / GM_K) <= GM_WS_MAXKB && !getenv("DPVO_B200_GEMM_STREAM");
+  // weight-stationary CTAs keep their column slice: the grid must be a multiple of the slice count
+  int64_t grid = std::min<int64_t>(tiles, sm_count());
+  if (ws) grid = std::max<int64_t>(n_tiles_n, grid / n_tiles_n * n_tiles_n);
+  CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
+  int rc = make_tmap(&tmB, a.W, a.N, a.K, a.ldw, GM_N);
+  if (rc) return rc;
+  if (a.gather) return ws ? launch_variant<true, true>(tmA, tmB, a, (unsigned)grid, st) : launch_variant<true, false>(tmA, tmB, a, (unsigned)grid, st);
+  rc = make_tmap(&tmA, a.X, a.rows, a.K, a.ldx, GM_M);
+  if (rc) return rc;
+  return ws ? launch_variant<false, true>(tmA, tmB, a, (unsigned)grid, st) : launch_variant<false, false>(tmA, tmB, a, (unsigned)grid, st);
 }
 
 extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather, const void* W, int64_t ldw,
@@ -441,7 +448,7 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
   if (rows == 0) return DPVO_OK;
   DPVO_REQUIRE(X && W && Y, "linear_f16: null pointer");
   DPVO_REQUIRE(K % GM_K == 0, "linear_f16: K=%d must be a multiple of %d (pad the operands)", K, GM_K);
-  DPVO_REQUIRE(N % 16 == 0, "linear_f16: N=%d must be a multiple of 16", N);
+  DPVO_REQUIRE(N % 32 == 0, "linear_f16: N=%d must be a multiple of 32", N);
   DPVO_REQUIRE(rows < (1ll << 31), "linear_f16: too many rows");
   DPVO_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)W & 15) == 0,
                "linear_f16: X / W rows must be 16-byte aligned");
@@ -458,7 +465,6 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
   DPVO_REQUIRE(!Y16 || (ldy16 % 8 == 0 && ((uintptr_t)Y16 & 15) == 0), "linear_f16: Y16 rows must be 16-byte aligned");
   a.Y16 = (__half*)Y16; a.ldy16 = ldy16;
   a.Y = Y; a.y_dtype = y_dtype; a.ldy = ldy; a.rows = rows; a.N = N; a.K = K; a.epilogue = epilogue;
-  { const char* e = getenv("DPVO_B200_EPI_STYLE"); a.epi_style = e ? atoi(e) : 1; }
-  if (N % 32 != 0) a.epi_style = 0;
+
   return linear_launch(a, (cudaStream_t)stream);
 }

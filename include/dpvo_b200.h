@@ -333,7 +333,7 @@ int dpvo_update_heads(const void* net32, const float* W4, const float* b4, const
  *   DPVO_EPI_GATEDRES  y = res + gate * (acc + bias)              (gate: [rows, N] fp16, stride ldgate)
  * Y dtype y_dtype (F16 or F32), row stride ldy; Y16 (optional) receives an fp16 copy of the same
  * result (row stride ldy16) so a following layer can consume it without another pass.  Y may alias
- * res.  K % 64 == 0 (pad 882 -> 896 with zeros), N % 16 == 0.  Row tails are handled.
+ * res.  K % 64 == 0 (pad 882 -> 896 with zeros), N % 32 == 0.  Row tails are handled.
  */
 #define DPVO_EPI_NONE     0
 #define DPVO_EPI_RELU     1

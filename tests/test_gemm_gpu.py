@@ -23,7 +23,7 @@ def _ref(x, w, b, epi, res=None, gate=None, gather=None):
     return y
 
 
-@pytest.mark.parametrize("rows,N,K", [(128, 192, 64), (1000, 384, 384), (4097, 384, 896), (300, 768, 384), (47712, 384, 384), (5, 16, 64)])
+@pytest.mark.parametrize("rows,N,K", [(128, 192, 64), (1000, 384, 384), (4097, 384, 896), (300, 768, 384), (47712, 384, 384), (5, 32, 64)])
 @pytest.mark.parametrize("epi", [0, 1, 2])
 def test_linear_plain(ext, rows, N, K, epi):
     g = torch.Generator(device=DEV).manual_seed(rows + N + K + epi)
@@ -64,7 +64,7 @@ def test_linear_gather_residual_gate(ext):
 
 def test_linear_no_bias_and_bad_shapes(ext):
     x = torch.randn(64, 128, device=DEV).half()
-    w = torch.randn(32, 128, device=DEV).half()
+    w = torch.randn(64, 128, device=DEV).half()
     y = ext[3].linear_f16(x, w, None, 0)
     assert (y[0].float() - x.float() @ w.float().t()).abs().max().item() < 5e-2
     with pytest.raises(RuntimeError):
