@@ -45,6 +45,7 @@ struct BaArgs {
   float* uk;      // [M]
   float* rec;     // [Gp][90]
   float* dX;      // [6N]
+  long long* dbg; // optional phase timestamps of the solve kernel (cluster rank 0), NULL = off
 };
 
 // ---- Eigen-free SE3 helpers, same formulas as ba_cuda.cu:36-174 -------------------------
@@ -342,6 +343,8 @@ ba_solve_kernel(const BaArgs a) {
   const int P = a.P;
   const int per = (Gk + BA_CLUSTER - 1) / BA_CLUSTER;
   const int m0 = min(Gk, rank * per), m1 = min(Gk, m0 + per);
+#define BA_STAMP(i) do { if (a.dbg && rank == 0 && tid == 0) a.dbg[i] = clock64(); } while (0)
+  BA_STAMP(0);
 
   if (N > 0) {
     for (int o = tid; o < (N6 + 1) * N6; o += BA_SOLVE_THREADS) sm.S[o / N6][o % N6] = 0.0f;
@@ -380,6 +383,7 @@ ba_solve_kernel(const BaArgs a) {
       }
       __syncthreads();
     }
+    BA_STAMP(1);
     // ---- 1b. pose blocks from this CTA's share of the pair records (pairs rank, rank+8, ...)
     const int Gp = *a.p_n;
     const int n_mine = (Gp > rank) ? (Gp - rank + BA_CLUSTER - 1) / BA_CLUSTER : 0;
@@ -434,7 +438,9 @@ ba_solve_kernel(const BaArgs a) {
       __syncthreads();
     }
   }
+  BA_STAMP(2);
   cluster.sync();
+  BA_STAMP(3);
 
   if (N > 0 && rank == 0) {
     // ---- 2. fixed-order reduction over distributed shared memory; mirror into the lower triangle
@@ -448,7 +454,9 @@ ba_solve_kernel(const BaArgs a) {
       if (row < N6) sm.S[col][row] = s;
     }
   }
+  BA_STAMP(4);
   cluster.sync();   // peers may now reuse their shared memory
+  BA_STAMP(5);
 
   if (N > 0 && rank == 0) {
     // ---- 3. blocked Cholesky of [S; y^T] (lower storage, row N6 = rhs): 6-column panels
@@ -493,6 +501,7 @@ ba_solve_kernel(const BaArgs a) {
       }
       __syncthreads();
     }
+    BA_STAMP(6);
     // row N6 now holds z = L^-1 y; back substitution L^T x = z with one warp
     if (tid < 32) {
       for (int k = N6 - 1; k >= 0; --k) {
@@ -506,7 +515,9 @@ ba_solve_kernel(const BaArgs a) {
     __syncthreads();
     for (int i = tid; i < N6; i += BA_SOLVE_THREADS) a.dX[i] = sm.dx[i];
   }
+  BA_STAMP(7);
   cluster.sync();
+  BA_STAMP(8);
 
   // ---- 4. depth back-substitution dZ = Q (u - E^T dX) and patch retraction (ba_cuda.cu:209-229)
   float* dxs = sm.Qt;      // reuse: per-CTA copy of dX needs N6 <= 192 floats -> use the Et area instead
@@ -531,8 +542,10 @@ ba_solve_kernel(const BaArgs a) {
     __syncwarp();
     if (lane < P * P) pd[lane] = d;
   }
+  BA_STAMP(9);
   // ---- 5. pose retraction (ba_cuda.cu:178-206), after every CTA is done reading dx
   cluster.sync();
+  BA_STAMP(10);
   if (N > 0 && rank == 0 && tid < N) {
     float* pp = a.poses + (int64_t)(a.t0 + tid) * 7;
     const float t[3] = {pp[0], pp[1], pp[2]}, q[4] = {pp[3], pp[4], pp[5], pp[6]};
@@ -636,6 +649,10 @@ extern "C" int64_t dpvo_ba_workspace_bytes(int64_t E, int n_free_poses) {
 }
 
 static int ba_run(BaArgs& a, int iterations, cudaStream_t st) {
+  static long long* dbg = nullptr;
+  const bool timing = getenv("DPVO_B200_BA_TIMING") != nullptr;
+  if (timing && !dbg) cudaMalloc(&dbg, 16 * sizeof(long long));
+  a.dbg = timing ? dbg : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveSmem));
@@ -648,6 +665,15 @@ static int ba_run(BaArgs& a, int iterations, cudaStream_t st) {
     DPVO_LAUNCH_CHECK("ba_reduce_kernel");
     ba_solve_kernel<<<BA_CLUSTER, BA_SOLVE_THREADS, sizeof(SolveSmem), st>>>(a);
     DPVO_LAUNCH_CHECK("ba_solve_kernel");
+  }
+  if (timing) {
+    long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const char* names[10] = {"schur", "pair blocks", "-> cluster.sync", "sync", "dsmem reduce", "sync", "cholesky", "back-subst", "sync", "depth update"};
+    fprintf(stderr, "[ba_solve phases, SM cycles]");
+    for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%lld", names[i], h[i + 1] - h[i]);
+    fprintf(stderr, " total=%lld\n", h[10] - h[0]);
   }
   return DPVO_OK;
 }

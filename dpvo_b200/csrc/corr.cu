@@ -244,6 +244,7 @@ struct __align__(16) MmaWarpSmem {
     __half patch[9 * MMA_PATP];       // 2448 B
     float raw[2][9 * MMA_RAWP + 3];   // per level: raw[p][box pixel] = <patch pixel p, box pixel>
   };
+  uint32_t stage[444];                // blended outputs of one edge as half2 (level0, level1), output order
   float4 w[2][9];                     // bilinear weights (1-dx)(1-dy), dx(1-dy), (1-dx)dy, dx dy
   int base[2][9];                     // index of tap (0,0) of pixel p inside its box
   int pitch[2][9];                    // row pitch of that box (bw, or 8 in the per-pixel fallback)
@@ -354,15 +355,13 @@ corr_fwd_mma(const CorrArgs a) {
           wx += 8; if (wx >= bw) { wx -= bw; ++wy; }          // 8 <= bw <= 10: at most one wrap
         };
 
-        uint4 Qc[4], Qn[4];
-        load_tile(Qc, g);
-        for (int nt = 0; nt < ntiles; ++nt) {
-          if (nt + 1 < ntiles) load_tile(Qn, (nt + 1) * 8 + g);
+        // one 8-pixel tile: 8 HMMAs (two independent accumulation chains) + dense store of the 16x8 block
+        auto mma_tile = [&](const uint4 (&Q)[4], int nt) {
           float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
-            mma16816(acc0, PA[kb].x, PB[kb].x, PA[kb].y, PB[kb].y, Qc[kb].x, Qc[kb].y);
-            mma16816(acc1, PA[kb].z, PB[kb].z, PA[kb].w, PB[kb].w, Qc[kb].z, Qc[kb].w);
+            mma16816(acc0, PA[kb].x, PB[kb].x, PA[kb].y, PB[kb].y, Q[kb].x, Q[kb].y);
+            mma16816(acc1, PA[kb].z, PB[kb].z, PA[kb].w, PB[kb].w, Q[kb].z, Q[kb].w);
           }
           // rows of the accumulator tile = patch pixels g (c0,c1) and 8 (c2,c3; g==0 lanes);
           // columns = box pixels nt*8 + 2t, +1: stored densely, no per-tap logic
@@ -371,41 +370,68 @@ corr_fwd_mma(const CorrArgs a) {
             *reinterpret_cast<float2*>(&raw[g * MMA_RAWP + col + (g & 1)]) = make_float2(acc0[0] + acc1[0], acc0[1] + acc1[1]);
           if (g == 0 && (uni || pass == 8))
             *reinterpret_cast<float2*>(&raw[8 * MMA_RAWP + col]) = make_float2(acc0[2] + acc1[2], acc0[3] + acc1[3]);
+        };
+        // software pipeline with two register buffers used alternately (no register copies)
+        uint4 Q0[4], Q1[4];
+        load_tile(Q0, g);
+        for (int nt = 0; nt < ntiles; nt += 2) {
+          if (nt + 1 < ntiles) load_tile(Q1, (nt + 1) * 8 + g);
+          mma_tile(Q0, nt);
           if (nt + 1 < ntiles) {
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb) Qc[kb] = Qn[kb];
+            if (nt + 2 < ntiles) load_tile(Q0, (nt + 2) * 8 + g);
+            mma_tile(Q1, nt + 1);
           }
         }
       }
     }
     __syncwarp();
 
-    // ---- bilinear blend of both levels + write (q = output element, p = q % 9, tap = q / 9)
-#pragma unroll 2
-    for (int i = 0; i < 14; ++i) {
-      const int q = lane + 32 * i;
-      if (q < NOUT) {
-        const int tt = (q * 3641) >> 15;            // q / 9 for q < 4096
-        const int p = q - 9 * tt;
-        const int xo = (tt * 37) >> 8;              // tt / 7 for tt < 56
-        const int yo = tt - 7 * xo;
-        float v[2];
+    // ---- bilinear blend of both levels.  Lanes own taps (two per lane, constant for the whole kernel),
+    // the loop runs over the nine patch pixels, so box pitch / base / weights are warp-uniform and the
+    // per-output cost is one multiply-add of indices, four shared loads and four FMAs.  Results are
+    // staged in shared memory in output order and copied out with 16-byte stores.
+    {
+      __half2* stage = reinterpret_cast<__half2*>(sm.stage);
+      const int tt0 = lane, tt1 = lane + 32;                  // taps 0..48 ; tap = xo*7 + yo
+      const int xo0 = (tt0 * 37) >> 8, yo0 = tt0 - 7 * xo0;
+      const int xo1 = (tt1 * 37) >> 8, yo1 = tt1 - 7 * xo1;
+#pragma unroll 1
+      for (int p = 0; p < 9; ++p) {
+        float v0[2] = {0.f, 0.f}, v1[2] = {0.f, 0.f};
 #pragma unroll
         for (int lev = 0; lev < 2; ++lev) {
           if (lev < a.nlev) {
             const int pitch = sm.pitch[lev][p];
             const float4 w = sm.w[lev][p];
-            const float* rp = &sm.raw[lev][p * MMA_RAWP + (p & 1) + sm.base[lev][p] + yo * pitch + xo];
-            v[lev] = w.x * rp[0] + w.y * rp[1] + w.z * rp[pitch] + w.w * rp[pitch + 1];
+            const float* rb = &sm.raw[lev][p * MMA_RAWP + (p & 1) + sm.base[lev][p]];
+            const float* r0 = rb + yo0 * pitch + xo0;
+            v0[lev] = w.x * r0[0] + w.y * r0[1] + w.z * r0[pitch] + w.w * r0[pitch + 1];
+            if (tt1 < 49) {
+              const float* r1 = rb + yo1 * pitch + xo1;
+              v1[lev] = w.x * r1[0] + w.y * r1[1] + w.z * r1[pitch] + w.w * r1[pitch + 1];
+            }
           }
         }
-        if constexpr (PAIR_OUT) {
-          reinterpret_cast<__half2*>(out + (int64_t)(b * a.M + m) * a.out_row)[q] = __floats2half2_rn(v[0], v[1]);
-        } else {
-          for (int lev = 0; lev < a.nlev; ++lev)
-            out[(int64_t)(b * a.M + m) * a.out_row + (int64_t)q * a.out_stride + a.out_offset[lev]] = __float2half_rn(v[lev]);
-        }
+        stage[tt0 * 9 + p] = __floats2half2_rn(v0[0], v0[1]);
+        if (tt1 < 49) stage[tt1 * 9 + p] = __floats2half2_rn(v1[0], v1[1]);
       }
+      __syncwarp();
+      if constexpr (PAIR_OUT) {
+        __half* orow = out + (int64_t)(b * a.M + m) * a.out_row;
+        if ((a.out_row & 7) == 0) {                            // 16-byte aligned rows (e.g. padded to 896)
+          const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+          for (int i = lane; i < (NOUT * 4) / 16; i += 32) reinterpret_cast<uint4*>(orow)[i] = s4[i];
+          if (lane == 0) reinterpret_cast<__half2*>(orow)[NOUT - 1] = stage[NOUT - 1];      // 441 = 4*110 + 1
+        } else {
+          for (int q = lane; q < NOUT; q += 32) reinterpret_cast<__half2*>(orow)[q] = stage[q];
+        }
+      } else {
+        const __half* sh = reinterpret_cast<const __half*>(stage);
+        for (int lev = 0; lev < a.nlev; ++lev)
+          for (int q = lane; q < NOUT; q += 32)
+            out[(int64_t)(b * a.M + m) * a.out_row + (int64_t)q * a.out_stride + a.out_offset[lev]] = sh[2 * q + lev];
+      }
+      __syncwarp();
     }
   }
 }

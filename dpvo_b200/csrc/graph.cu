@@ -14,15 +14,19 @@
 namespace dpvo {
 
 constexpr int G_THREADS = 256;
-constexpr int G_ITEMS = 8;
-constexpr int G_TILE = G_THREADS * G_ITEMS;   // 2048 edge slots per tile
+constexpr int G_ITEMS = 4;
+constexpr int G_TILE = G_THREADS * G_ITEMS;   // 1024 edge slots per tile
 constexpr int G_WARPS = G_THREADS / 32;
-constexpr int G_BINS = 256;
+constexpr int G_MAXBITS = 10;                 // radix digit width is chosen per sort, <= 10 bits
+constexpr int G_BINS = 1 << G_MAXBITS;
+constexpr int G_MAXPASS = 20;
 
-struct GroupHeader {            // lives at the start of the workspace
-  unsigned barrier;             // must be 0 at launch (memset by the host wrapper)
-  int npass[3];                 // radix passes for sec / key_b / key_a
-  long long amin, amax, bmin, bmax, smin, smax;
+// Header at the start of the workspace; the host wrapper memsets it to zero before the launch.
+// Ranges are tracked as unsigned maxima of the order-preserving bias u = x ^ 2^63 and of ~u (giving
+// the minimum), so zero is a valid initial value and no initialisation phase is needed.
+struct GroupHeader {
+  unsigned barrier; unsigned pad;
+  unsigned long long amax, anmax, bmax, bnmax, smax, snmax;
 };
 
 struct GroupArgs {
@@ -51,14 +55,12 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch) {
   __syncthreads();
 }
 
-__device__ __forceinline__ int bits_needed(long long range) {   // range >= 0
-  int b = 0;
-  while (range > 0) { ++b; range >>= 1; }
-  return b;
+__device__ __forceinline__ int bits_needed(unsigned long long range) {
+  return range == 0 ? 0 : 64 - __clzll(range);
 }
+__device__ __forceinline__ unsigned long long bias64(long long x) { return (unsigned long long)x ^ 0x8000000000000000ull; }
 
-// exclusive scan of one int per thread across the block; returns the exclusive prefix and the
-// block total
+// exclusive scan of one int per thread across the block; returns the exclusive prefix and the total
 __device__ __forceinline__ int block_excl_scan(int v, int* smem_warp /*[G_WARPS+1]*/, int& total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int inc = v;
@@ -80,141 +82,163 @@ __device__ __forceinline__ int block_excl_scan(int v, int* smem_warp /*[G_WARPS+
   return smem_warp[w] + inc - v;
 }
 
+// One persistent kernel: ranges -> [count, scatter] per radix pass -> boundary flags -> group ids.
+// Two grid barriers per pass (every block derives its own scatter offsets from the tile-major
+// histogram instead of waiting for a scan block), one after the ranges, one before the final phase.
 __global__ void __launch_bounds__(G_THREADS)
 group_edges_kernel(const GroupArgs a) {
   __shared__ unsigned warp_hist[G_WARPS][G_BINS];
   __shared__ int scan_tmp[G_WARPS + 1];
-  __shared__ long long red[6];
+  __shared__ unsigned long long red[6];
+  __shared__ int p_field[G_MAXPASS], p_shift[G_MAXPASS], p_bits[G_MAXPASS], n_pass;
   unsigned epoch = 0;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   GroupHeader* H = a.hdr;
   const int64_t E = a.E;
 
-  // ---- phase 0a: initialise the header
-  if (blockIdx.x == 0 && tid == 0) {
-    H->amin = H->bmin = H->smin = 0x7fffffffffffffffLL;
-    H->amax = H->bmax = H->smax = -0x7fffffffffffffffLL - 1;
-  }
-  grid_barrier(&H->barrier, epoch);
-
-  // ---- phase 0b: value ranges, identity permutation
+  // ---- phase 0: value ranges, identity permutation
   {
-    long long mn[3] = {0x7fffffffffffffffLL, 0x7fffffffffffffffLL, 0x7fffffffffffffffLL};
-    long long mx[3] = {-0x7fffffffffffffffLL - 1, -0x7fffffffffffffffLL - 1, -0x7fffffffffffffffLL - 1};
+    unsigned long long mx[6] = {0, 0, 0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * G_THREADS + tid; i < E; i += (int64_t)gridDim.x * G_THREADS) {
       a.buf0[i] = (int32_t)i;
-      const long long va = a.ka[i];
-      mn[0] = min(mn[0], va); mx[0] = max(mx[0], va);
-      if (a.kb) { const long long vb = a.kb[i]; mn[1] = min(mn[1], vb); mx[1] = max(mx[1], vb); }
-      if (a.sec) { const long long vs = a.sec[i]; mn[2] = min(mn[2], vs); mx[2] = max(mx[2], vs); }
+      const unsigned long long ua = bias64(a.ka[i]);
+      mx[0] = max(mx[0], ua); mx[1] = max(mx[1], ~ua);
+      if (a.kb) { const unsigned long long ub = bias64(a.kb[i]); mx[2] = max(mx[2], ub); mx[3] = max(mx[3], ~ub); }
+      if (a.sec) { const unsigned long long us = bias64(a.sec[i]); mx[4] = max(mx[4], us); mx[5] = max(mx[5], ~us); }
     }
-    if (tid < 6) red[tid] = (tid < 3) ? 0x7fffffffffffffffLL : (-0x7fffffffffffffffLL - 1);
+    if (tid < 6) red[tid] = 0ull;
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 6; ++k) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        mn[k] = min(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-        mx[k] = max(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-      }
-      if (lane == 0) { atomicMin(&red[k], mn[k]); atomicMax(&red[3 + k], mx[k]); }
+      for (int o = 16; o > 0; o >>= 1) mx[k] = max(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+      if (lane == 0) atomicMax(&red[k], mx[k]);
     }
     __syncthreads();
-    if (tid == 0) {
-      atomicMin(&H->amin, red[0]); atomicMax(&H->amax, red[3]);
-      if (a.kb) { atomicMin(&H->bmin, red[1]); atomicMax(&H->bmax, red[4]); }
-      if (a.sec) { atomicMin(&H->smin, red[2]); atomicMax(&H->smax, red[5]); }
-    }
+    if (tid < 6) atomicMax(&H->amax + tid, red[tid]);
   }
   grid_barrier(&H->barrier, epoch);
 
-  const long long amin = H->amin, bmin = a.kb ? H->bmin : 0, smin = a.sec ? H->smin : 0;
-  int npass[3];
-  npass[0] = a.sec ? (bits_needed(H->smax - smin) + 7) / 8 : 0;
-  npass[1] = a.kb ? (bits_needed(H->bmax - bmin) + 7) / 8 : 0;
-  npass[2] = (bits_needed(H->amax - amin) + 7) / 8;
+  const unsigned long long amin = ~H->anmax, bmin = a.kb ? ~H->bnmax : 0, smin = a.sec ? ~H->snmax : 0;
+  const int abits = bits_needed(H->amax - amin);
+  const int bbits = a.kb ? bits_needed(H->bmax - bmin) : 0;
+  const int sbits = a.sec ? bits_needed(H->smax - smin) : 0;
+  const bool composite = abits + bbits + sbits <= 64;
+  if (tid == 0) {
+    // pass table (least significant first).  composite: one key  a_rel << (bbits+sbits) | b_rel << sbits | s_rel
+    int np = 0;
+    auto add_field = [&](int field, int bits) {
+      if (bits == 0) return;
+      const int passes = (bits + G_MAXBITS - 1) / G_MAXBITS, per = (bits + passes - 1) / passes;
+      for (int sh = 0; sh < bits; sh += per) { p_field[np] = field; p_shift[np] = sh; p_bits[np] = min(per, bits - sh); ++np; }
+    };
+    if (composite) add_field(3, abits + bbits + sbits);
+    else { add_field(0, sbits); add_field(1, bbits); add_field(2, abits); }
+    n_pass = np;
+  }
+  __syncthreads();
+
+  auto key_of = [&](int32_t e, int field) -> unsigned long long {
+    if (field == 3) {
+      unsigned long long k = bias64(a.ka[e]) - amin;
+      if (a.kb) k = (k << bbits) | (bias64(a.kb[e]) - bmin);
+      if (a.sec) k = (k << sbits) | (bias64(a.sec[e]) - smin);
+      return k;
+    }
+    if (field == 0) return bias64(a.sec[e]) - smin;
+    if (field == 1) return bias64(a.kb[e]) - bmin;
+    return bias64(a.ka[e]) - amin;
+  };
 
   int32_t* src = a.buf0;
   int32_t* dst = a.buf1;
+  const int npass = n_pass;
 
-  // ---- radix passes: sec (least significant field) -> key_b -> key_a
-  for (int field = 0; field < 3; ++field) {
-    const int64_t* vals = field == 0 ? a.sec : (field == 1 ? a.kb : a.ka);
-    const long long vmin = field == 0 ? smin : (field == 1 ? bmin : amin);
-    for (int pass = 0; pass < npass[field]; ++pass) {
-      const int shift = 8 * pass;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int field = p_field[pass], shift = p_shift[pass], nbins = 1 << p_bits[pass];
+    const unsigned mask = (unsigned)nbins - 1u;
 
-      // count: stable per-warp digit histograms of every tile this block owns
-      for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-        for (int i = tid; i < G_WARPS * G_BINS; i += G_THREADS) (&warp_hist[0][0])[i] = 0u;
-        __syncthreads();
-        const int64_t base = (int64_t)t * G_TILE + w * (G_TILE / G_WARPS);
-        for (int c = 0; c < G_TILE / G_WARPS / 32; ++c) {
-          const int64_t i = base + c * 32 + lane;
-          unsigned d = 0xffffffffu;
-          if (i < E) d = (unsigned)(((unsigned long long)(vals[src[i]] - vmin) >> shift) & 255ull);
-          const unsigned peers = __match_any_sync(0xffffffffu, d);
-          if (d != 0xffffffffu && lane == __ffs(peers) - 1) warp_hist[w][d] += __popc(peers);
-          __syncwarp();
-        }
-        __syncthreads();
-        unsigned s = 0;
+    // per-warp stable digit histograms of one tile (warp w owns 128 consecutive slots)
+    auto warp_count = [&](int t) {
+      for (int i = tid; i < G_WARPS * nbins; i += G_THREADS) warp_hist[i / nbins][i % nbins] = 0u;
+      __syncthreads();
+      const int64_t base = (int64_t)t * G_TILE + w * (G_TILE / G_WARPS);
 #pragma unroll
-        for (int k = 0; k < G_WARPS; ++k) s += warp_hist[k][tid];
-        a.hist[(size_t)tid * a.ntiles + t] = s;
-        __syncthreads();
+      for (int c = 0; c < G_TILE / G_WARPS / 32; ++c) {
+        const int64_t i = base + c * 32 + lane;
+        unsigned d = 0xffffffffu;
+        if (i < E) d = (unsigned)(key_of(src[i], field) >> shift) & mask;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (d != 0xffffffffu && lane == __ffs(peers) - 1) warp_hist[w][d] += __popc(peers);
+        __syncwarp();
       }
-      grid_barrier(&H->barrier, epoch);
+      __syncthreads();
+    };
 
-      // scan (block 0): exclusive prefix over hist in bin-major order
-      if (blockIdx.x == 0) {
-        unsigned* h = a.hist + (size_t)tid * a.ntiles;
-        int tot = 0;
-        for (int t = 0; t < a.ntiles; ++t) tot += (int)h[t];
-        int all;
-        int run = block_excl_scan(tot, scan_tmp, all);
-        for (int t = 0; t < a.ntiles; ++t) { const unsigned v = h[t]; h[t] = (unsigned)run; run += (int)v; }
-      }
-      grid_barrier(&H->barrier, epoch);
-
-      // scatter
-      for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-        for (int i = tid; i < G_WARPS * G_BINS; i += G_THREADS) (&warp_hist[0][0])[i] = 0u;
-        __syncthreads();
-        const int64_t base = (int64_t)t * G_TILE + w * (G_TILE / G_WARPS);
-        for (int c = 0; c < G_TILE / G_WARPS / 32; ++c) {
-          const int64_t i = base + c * 32 + lane;
-          unsigned d = 0xffffffffu;
-          if (i < E) d = (unsigned)(((unsigned long long)(vals[src[i]] - vmin) >> shift) & 255ull);
-          const unsigned peers = __match_any_sync(0xffffffffu, d);
-          if (d != 0xffffffffu && lane == __ffs(peers) - 1) warp_hist[w][d] += __popc(peers);
-          __syncwarp();
-        }
-        __syncthreads();
-        {   // per-bin exclusive prefix over the warps, offset by the global position of (bin, tile)
-          unsigned run = a.hist[(size_t)tid * a.ntiles + t];
+    // ---- count
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+      warp_count(t);
+      for (int b = tid; b < nbins; b += G_THREADS) {
+        unsigned sum = 0;
 #pragma unroll
-          for (int k = 0; k < G_WARPS; ++k) { const unsigned v = warp_hist[k][tid]; warp_hist[k][tid] = run; run += v; }
-        }
-        __syncthreads();
-        for (int c = 0; c < G_TILE / G_WARPS / 32; ++c) {
-          const int64_t i = base + c * 32 + lane;
-          unsigned d = 0xffffffffu;
-          int32_t id = 0;
-          if (i < E) { id = src[i]; d = (unsigned)(((unsigned long long)(vals[id] - vmin) >> shift) & 255ull); }
-          const unsigned peers = __match_any_sync(0xffffffffu, d);
-          const int leader = __ffs(peers) - 1;
-          unsigned pos = 0;
-          if (d != 0xffffffffu && lane == leader) { pos = warp_hist[w][d]; warp_hist[w][d] = pos + __popc(peers); }
-          pos = __shfl_sync(0xffffffffu, pos, leader);
-          if (d != 0xffffffffu) dst[pos + __popc(peers & ((1u << lane) - 1u))] = id;
-          __syncwarp();
-        }
-        __syncthreads();
+        for (int k = 0; k < G_WARPS; ++k) sum += warp_hist[k][b];
+        a.hist[(size_t)t * G_BINS + b] = sum;
       }
-      grid_barrier(&H->barrier, epoch);
-      int32_t* tmp = src; src = dst; dst = tmp;
+      __syncthreads();
     }
+    grid_barrier(&H->barrier, epoch);
+
+    // ---- scatter: every block derives the offsets of its own tiles from the tile-major histogram
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+      warp_count(t);
+      const int bpt = (nbins + G_THREADS - 1) / G_THREADS;      // contiguous bins per thread
+      unsigned before[G_BINS / G_THREADS], total[G_BINS / G_THREADS];
+      int mine = 0;
+#pragma unroll
+      for (int k = 0; k < G_BINS / G_THREADS; ++k) {
+        before[k] = 0; total[k] = 0;
+        const int b = tid * bpt + k;
+        if (k < bpt && b < nbins) {
+          for (int tt = 0; tt < a.ntiles; ++tt) {
+            const unsigned v = a.hist[(size_t)tt * G_BINS + b];
+            if (tt < t) before[k] += v;
+            total[k] += v;
+          }
+          mine += (int)total[k];
+        }
+      }
+      int all;
+      unsigned run = (unsigned)block_excl_scan(mine, scan_tmp, all);      // bins are contiguous per thread
+#pragma unroll
+      for (int k = 0; k < G_BINS / G_THREADS; ++k) {
+        const int b = tid * bpt + k;
+        if (k < bpt && b < nbins) {
+          unsigned o = run + before[k];
+          run += total[k];
+#pragma unroll
+          for (int q = 0; q < G_WARPS; ++q) { const unsigned v = warp_hist[q][b]; warp_hist[q][b] = o; o += v; }
+        }
+      }
+      __syncthreads();
+      const int64_t base = (int64_t)t * G_TILE + w * (G_TILE / G_WARPS);
+#pragma unroll
+      for (int c = 0; c < G_TILE / G_WARPS / 32; ++c) {
+        const int64_t i = base + c * 32 + lane;
+        unsigned d = 0xffffffffu;
+        int32_t id = 0;
+        if (i < E) { id = src[i]; d = (unsigned)(key_of(id, field) >> shift) & mask; }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        unsigned pos = 0;
+        if (d != 0xffffffffu && lane == leader) { pos = warp_hist[w][d]; warp_hist[w][d] = pos + __popc(peers); }
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (d != 0xffffffffu) dst[pos + __popc(peers & ((1u << lane) - 1u))] = id;
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+    grid_barrier(&H->barrier, epoch);
+    int32_t* tmp = src; src = dst; dst = tmp;
   }
 
   // ---- boundaries: flag[i] = first position of a new (key_a, key_b) group
@@ -236,29 +260,25 @@ group_edges_kernel(const GroupArgs a) {
     __syncthreads();
   }
   grid_barrier(&H->barrier, epoch);
-  if (blockIdx.x == 0) {
-    // exclusive scan of tile_sums, chunked through the block
-    int carry = 0;
-    for (int t0 = 0; t0 < a.ntiles; t0 += G_THREADS) {
-      const int t = t0 + tid;
-      const int v = (t < a.ntiles) ? a.tile_sums[t] : 0;
-      int total;
-      const int ex = block_excl_scan(v, scan_tmp, total);
-      if (t < a.ntiles) a.tile_sums[t] = carry + ex;
-      carry += total;
-      __syncthreads();
-    }
-    if (tid == 0) { *a.n_groups = carry; a.group_start[carry] = (int32_t)E; }
-  }
-  grid_barrier(&H->barrier, epoch);
   for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+    // groups before this tile (and, for the block owning tile 0, the grand total)
+    int part = 0, whole = 0;
+    for (int tt = tid; tt < a.ntiles; tt += G_THREADS) {
+      const int v = a.tile_sums[tt];
+      whole += v;
+      if (tt < t) part += v;
+    }
+    int tot_part, tot_whole;
+    block_excl_scan(part, scan_tmp, tot_part);
+    block_excl_scan(whole, scan_tmp, tot_whole);
+    if (t == 0 && tid == 0) { *a.n_groups = tot_whole; a.group_start[tot_whole] = (int32_t)E; }
     int flags[G_ITEMS];
     int cnt = 0;
     const int64_t base = (int64_t)t * G_TILE + (int64_t)tid * G_ITEMS;
 #pragma unroll
     for (int k = 0; k < G_ITEMS; ++k) { flags[k] = (base + k < E) ? is_head(base + k) : 0; cnt += flags[k]; }
     int total;
-    int gid = a.tile_sums[t] + block_excl_scan(cnt, scan_tmp, total) - 1;
+    int gid = tot_part + block_excl_scan(cnt, scan_tmp, total) - 1;
 #pragma unroll
     for (int k = 0; k < G_ITEMS; ++k) {
       const int64_t i = base + k;
@@ -295,7 +315,7 @@ static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
 static int64_t group_ws_bytes(int64_t E) {
   const int64_t ntiles = (E + G_TILE - 1) / G_TILE;
-  return align256(sizeof(GroupHeader)) + 2 * align256(E * 4) + align256(ntiles * G_BINS * 4) + align256((ntiles + 1) * 4);
+  return align256(sizeof(GroupHeader)) + 2 * align256(E * 4) + align256(ntiles * (int64_t)G_BINS * 4) + align256((ntiles + 1) * 4);
 }
 
 static int group_launch(const int64_t* ka, const int64_t* kb, const int64_t* sec, int64_t E,
