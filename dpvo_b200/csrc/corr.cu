@@ -42,6 +42,8 @@ struct CorrArgs {
   int out_offset[2];    // element offset of each level inside one logical output slot
   int nlev;             // 1 or 2 levels handled by this launch
   int B, M, C, P, R;
+  const int* list;       // optional device list of edge ids to process (B == 1), with its length on device
+  const int* list_count;
 };
 
 // ==========================================================================================
@@ -264,13 +266,13 @@ corr_fwd_mma(const CorrArgs a) {
   extern __shared__ __align__(16) unsigned char mma_smem_raw[];
   MmaWarpSmem& sm = reinterpret_cast<MmaWarpSmem*>(mma_smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int64_t nitems = (int64_t)a.B * a.M;
+  const int64_t nitems = a.list ? (int64_t)*a.list_count : (int64_t)a.B * a.M;
   const int64_t wstride = (int64_t)gridDim.x * MMA_WARPS;
   const __half* f1 = reinterpret_cast<const __half*>(a.fmap1);
   __half* out = reinterpret_cast<__half*>(a.out);
 
   for (int64_t item = (int64_t)blockIdx.x * MMA_WARPS + (threadIdx.x >> 5); item < nitems; item += wstride) {
-    const int b = (int)(item / a.M), m = (int)(item % a.M);
+    const int b = a.list ? 0 : (int)(item / a.M), m = a.list ? a.list[item] : (int)(item % a.M);
     const int64_t ix = a.ii[m], jx = a.jj[m];
 
     // ---- patch features -> shared as [pixel][channel]
@@ -687,7 +689,8 @@ static int launch_mma(const CorrArgs& a, bool pair_out, cudaStream_t st) {
   const int64_t nitems = (int64_t)a.B * a.M;
   if (nitems == 0) return DPVO_OK;
   const int64_t need = (nitems + MMA_WARPS - 1) / MMA_WARPS;
-  const int64_t grid = std::min<int64_t>(need, (int64_t)sm_count() * 2);
+  // list mode: the length lives on the device; one CTA per SM drains it
+  const int64_t grid = std::min<int64_t>(need, (int64_t)sm_count() * (a.list ? 1 : 2));
   const size_t smem = sizeof(MmaWarpSmem) * MMA_WARPS;
   static bool attr = false;
   if (!attr) {
@@ -699,6 +702,26 @@ static int launch_mma(const CorrArgs& a, bool pair_out, cudaStream_t st) {
   else corr_fwd_mma<false><<<(unsigned)grid, MMA_WARPS * 32, smem, st>>>(a);
   DPVO_LAUNCH_CHECK("corr_fwd_mma");
   return DPVO_OK;
+}
+
+// corr_tc.cu
+int corr_tc_forward(const void* fmap1, const int64_t* s1, int S1, const void* l0, const int64_t* s20, int H0, int W0,
+                    const void* l1, const int64_t* s21, int H1, int W1, int S2, float div1, const float* coords,
+                    const int64_t* ii, const int64_t* jj, void* out, int64_t out_row, int M, void* scratch, cudaStream_t st);
+
+int corr_launch_fallback_list(const void* fmap1, const int64_t* s1, const void* l0, const int64_t* s20, int H0, int W0,
+                              const void* l1, const int64_t* s21, int H1, int W1, float div1, const float* coords,
+                              const int64_t* ii, const int64_t* jj, void* out, int64_t out_row, int M,
+                              const int* list, const int* count, cudaStream_t st) {
+  CorrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.fmap1 = fmap1; a.fmap2[0] = l0; a.fmap2[1] = l1;
+  for (int i = 0; i < 5; ++i) { a.s1[i] = s1[i]; a.s2[0][i] = s20[i]; a.s2[1][i] = s21[i]; }
+  a.H2[0] = H0; a.W2[0] = W0; a.H2[1] = H1; a.W2[1] = W1; a.div[0] = 1.0f; a.div[1] = div1;
+  a.coords = coords; a.ii = ii; a.jj = jj; a.out = out; a.out_stride = 2;
+  a.out_offset[0] = 0; a.out_offset[1] = 1; a.nlev = 2; a.B = 1; a.M = M; a.C = 128; a.P = 3; a.R = 3;
+  a.out_row = out_row; a.list = list; a.list_count = count;
+  return launch_mma(a, true, st);
 }
 
 static int corr_dispatch(const CorrArgs& a, int dtype, bool pair_out, cudaStream_t st) {
@@ -747,7 +770,8 @@ extern "C" int dpvo_corr_forward_pyramid2(const void* fmap1, const int64_t* fmap
                                           const float* coords, const int64_t* ii, const int64_t* jj,
                                           void* out, int64_t out_row_stride,
                                           int dtype, int B, int M, int C, int P,
-                                          int S1, int S2, int radius, void* stream) {
+                                          int S1, int S2, int radius,
+                                          void* workspace, int64_t workspace_bytes, void* stream) {
   DPVO_REQUIRE(B >= 0 && M >= 0 && C > 0 && P > 0 && radius >= 0 && H0 > 0 && W0 > 0 && H1 > 0 && W1 > 0,
                "corr_forward_pyramid2: bad sizes");
   DPVO_REQUIRE(lvl1_div > 0.f, "corr_forward_pyramid2: lvl1_div must be > 0");
@@ -756,7 +780,6 @@ extern "C" int dpvo_corr_forward_pyramid2(const void* fmap1, const int64_t* fmap
   if ((int64_t)B * M == 0) return DPVO_OK;
   DPVO_REQUIRE(fmap1 && fmap2_l0 && fmap2_l1 && coords && ii && jj && out && fmap1_strides && l0_strides && l1_strides,
                "corr_forward_pyramid2: null pointer");
-  (void)S1; (void)S2;
   CorrArgs a;
   memset(&a, 0, sizeof(a));
   a.fmap1 = fmap1; a.fmap2[0] = fmap2_l0; a.fmap2[1] = fmap2_l1;
@@ -765,8 +788,17 @@ extern "C" int dpvo_corr_forward_pyramid2(const void* fmap1, const int64_t* fmap
   a.coords = coords; a.ii = ii; a.jj = jj; a.out = out; a.out_stride = 2;
   a.out_offset[0] = 0; a.out_offset[1] = 1; a.nlev = 2; a.B = B; a.M = M; a.C = C; a.P = P; a.R = radius;
   a.out_row = out_row_stride;
+  // tcgen05 + TMA path: fp16 channels-last rings, batch 1, caller-provided scratch for the edge list
+  if (workspace && workspace_bytes >= dpvo_corr_pyramid2_workspace_bytes(M) && B == 1 && S1 > 0 && S2 > 0 &&
+      mma_eligible(a, dtype) && !getenv("DPVO_B200_CORR_GENERIC") && !getenv("DPVO_B200_CORR_MMA")) {
+    const int rc = corr_tc_forward(fmap1, a.s1, S1, fmap2_l0, a.s2[0], H0, W0, fmap2_l1, a.s2[1], H1, W1, S2, lvl1_div, coords, ii, jj,
+                                   out, out_row_stride, M, workspace, (cudaStream_t)stream);
+    if (rc != DPVO_ERR_UNSUPPORTED) return rc;
+  }
   return corr_dispatch(a, dtype, true, (cudaStream_t)stream);
 }
+
+extern "C" int64_t dpvo_corr_pyramid2_workspace_bytes(int64_t M) { return (M + 1) * (int64_t)sizeof(int) + 16; }
 
 extern "C" int dpvo_corr_backward(const void* fmap1, const int64_t* fmap1_strides,
                                   const void* fmap2, const int64_t* fmap2_strides,

@@ -283,11 +283,13 @@ Tensor corr_pyramid2(Tensor fmap1, Tensor fmap2_l0, Tensor fmap2_l1, Tensor coor
     out = (row == feat) ? torch::empty({B, M, O, O, P, P, 2}, fmap1.options()) : torch::zeros({B, M, row}, fmap1.options());
   }
   auto s1 = strides5(fmap1), s20 = strides5(fmap2_l0), s21 = strides5(fmap2_l1);
+  const int64_t wsb = dpvo_corr_pyramid2_workspace_bytes(M);
+  Tensor ws = torch::empty({wsb}, torch::dtype(torch::kUInt8).device(fmap1.device()));
   check(dpvo_corr_forward_pyramid2(fmap1.data_ptr(), s1.data(), fmap2_l0.data_ptr(), s20.data(), (int)fmap2_l0.size(3),
                                    (int)fmap2_l0.size(4), fmap2_l1.data_ptr(), s21.data(), (int)fmap2_l1.size(3),
                                    (int)fmap2_l1.size(4), (float)div, coords.data_ptr<float>(), ii.data_ptr<int64_t>(),
                                    jj.data_ptr<int64_t>(), out.data_ptr(), row, dt(fmap1), B, M, C, P, (int)fmap1.size(1),
-                                   (int)fmap2_l0.size(1), radius, stream()),
+                                   (int)fmap2_l0.size(1), radius, ws.data_ptr(), wsb, stream()),
         "dpvo_b200_ext.corr_pyramid2");
   return out;
 }

@@ -94,7 +94,13 @@ int dpvo_corr_forward_pyramid2(const void* fmap1, const int64_t* fmap1_strides,
                                const float* coords, const int64_t* ii, const int64_t* jj,
                                void* out, int64_t out_row_stride,
                                int dtype, int B, int M, int C, int P,
-                               int S1, int S2, int radius, void* stream);
+                               int S1, int S2, int radius,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+/* Scratch for the tcgen05/TMA kernel of dpvo_corr_forward_pyramid2 (list of edges whose nine tap windows do
+ * not fit one 10x10 box, finished by the mma.sync kernel).  workspace may be NULL: the call then runs the
+ * mma.sync kernel for every edge.  S1 / S2 are the slot counts of the patch-feature and frame-feature rings
+ * (extents of the TMA tensor maps). */
+int64_t dpvo_corr_pyramid2_workspace_bytes(int64_t M);
 
 /*
  * cuda_corr.backward -- correlation_kernel.cu:236-286 (bilinear-transpose :252-269 + kernel

@@ -86,25 +86,71 @@ def test_corr_empty(ext):
     assert out.shape == (1, 0, 7, 7, 3, 3)
 
 
-@pytest.mark.parametrize("dtype", [torch.half, torch.float32])
-def test_corr_pyramid2_matches_two_calls(ext, dtype):
-    """fused two-level entry == torch.stack of two single-level calls (dpvo.py:205-207)"""
-    g = torch.Generator().manual_seed(7)
-    S1, S2, H, W, M = 50, 4, 32, 48, 400
+def _pyramid_inputs(dtype, M, seed=7, S1=50, S2=4, H=32, W=48, stretch_every=0, fx=2.7, fy=2.7):
+    g = torch.Generator().manual_seed(seed)
     f1 = (torch.randn(1, S1, 3, 3, 128, generator=g) / 4).to(dtype).to(DEV).permute(0, 1, 4, 2, 3)
     l0 = (torch.randn(1, S2, H, W, 128, generator=g) / 4).to(dtype).to(DEV).permute(0, 1, 4, 2, 3)
     l1 = (torch.randn(1, S2, H // 4, W // 4, 128, generator=g) / 4).to(dtype).to(DEV).permute(0, 1, 4, 2, 3)
     coords = torch.zeros(1, M, 2, 3, 3)
     offs = torch.arange(3).float() - 1
-    coords[0, :, 0] = (torch.rand(M, generator=g) * (W + 8) - 4)[:, None, None] + offs[None, None, :]
-    coords[0, :, 1] = (torch.rand(M, generator=g) * (H + 8) - 4)[:, None, None] + offs[None, :, None]
-    coords = coords.to(DEV)
+    sx, sy = torch.ones(M), torch.ones(M)
+    if stretch_every:
+        sx[::stretch_every] = fx              # 2.7: the nine tap windows no longer fit any box of the tcgen05 kernel
+        sy[::stretch_every] = fy
+    coords[0, :, 0] = (torch.rand(M, generator=g) * (W + 8) - 4)[:, None, None] + offs[None, None, :] * sx[:, None, None]
+    coords[0, :, 1] = (torch.rand(M, generator=g) * (H + 8) - 4)[:, None, None] + offs[None, :, None] * sy[:, None, None]
     ii = torch.randint(0, S1, (M,), generator=g).to(DEV)
     jj = torch.randint(0, S2, (M,), generator=g).to(DEV)
+    return f1, l0, l1, coords.to(DEV), ii, jj
+
+
+@pytest.mark.parametrize("dtype", [torch.half, torch.float32])
+def test_corr_pyramid2_matches_two_calls(ext, dtype):
+    """fused two-level entry == torch.stack of two single-level calls (dpvo.py:205-207)"""
+    f1, l0, l1, coords, ii, jj = _pyramid_inputs(dtype, 400)
     a, = ext[0].forward(f1, l0, coords, ii, jj, 3)
     b, = ext[0].forward(f1, l1, coords / 4, ii, jj, 3)
     fused = ext[3].corr_pyramid2(f1, l0, l1, coords, ii, jj, 3, 4.0)
-    assert torch.equal(fused, torch.stack([a, b], -1))
+    ref = torch.stack([a, b], -1)
+    if dtype == torch.float32:
+        assert torch.equal(fused, ref)
+    else:
+        # fp16 features: the fused call runs on tcgen05 (fp32 accumulation in another order than mma.sync),
+        # results agree to fp16 rounding
+        assert torch.allclose(fused.float(), ref.float(), atol=2e-3, rtol=2e-3)
+
+
+@pytest.mark.parametrize("M,stretch,pad,fx,fy", [(1, 0, 0, 1, 1), (149, 3, 896, 2.7, 2.7), (5000, 7, 896, 2.7, 2.7), (3000, 0, 0, 1, 1),
+                                                 (3000, 2, 896, 1.4, 1.4), (3000, 2, 896, 1.9, 1.0), (3000, 3, 0, 0.6, 1.9),
+                                                 (2000, 2, 0, 1.9, 1.9), (2000, 2, 0, 0.3, 0.3)])
+def test_corr_tcgen05_vs_oracle(ext, M, stretch, pad, fx, fy):
+    """tcgen05/TMA kernel (every box shape 8..12 x 8..12 up to 128 pixels, the stretched-edge list finished by
+    the mma.sync kernel, out-of-map boxes zero-filled by TMA, padded rows) against the fp64 restatement of
+    correlation_kernel.cu:78-137"""
+    f1, l0, l1, coords, ii, jj = _pyramid_inputs(torch.half, M, seed=11 + M, stretch_every=stretch, fx=fx, fy=fy)
+    out = ext[3].corr_pyramid2(f1, l0, l1, coords, ii, jj, 3, 4.0, pad)
+    if pad:
+        assert out.shape == (1, M, pad)
+        assert torch.count_nonzero(out[..., 882:]) == 0
+        out = out[..., :882].reshape(1, M, 7, 7, 3, 3, 2)
+    c = coords.cpu()
+    want0 = OC.corr_forward(f1.cpu().double(), l0.cpu().double(), c, ii.cpu(), jj.cpu(), 3)
+    want1 = OC.corr_forward(f1.cpu().double(), l1.cpu().double(), c / 4, ii.cpu(), jj.cpu(), 3)
+    want = torch.stack([want0, want1], -1)
+    err = (out.cpu().double() - want).abs()
+    tol = 2.0 ** -10 * want.abs() + 1e-4 * want.abs().max()    # one fp16 rounding + fp32 accumulation noise
+    assert bool((err <= tol).all()), float((err - tol).max())
+
+
+def test_corr_tcgen05_far_outside(ext):
+    """boxes entirely outside the map (also by millions of pixels) give exact zeros"""
+    f1, l0, l1, coords, ii, jj = _pyramid_inputs(torch.half, 64)
+    coords[0, ::2] += 3.0e6
+    coords[0, 1::4] -= 5.0e8
+    out = ext[3].corr_pyramid2(f1, l0, l1, coords, ii, jj, 3, 4.0)
+    assert torch.count_nonzero(out[0, ::2]) == 0
+    assert torch.count_nonzero(out[0, 1::4]) == 0
+    assert torch.isfinite(out).all()
 
 
 @pytest.mark.parametrize("cl", [False, True])
