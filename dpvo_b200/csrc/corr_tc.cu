@@ -15,12 +15,13 @@
 //     <box pixel, patch pixel> for all pairs into 16 TMEM columns per level
 //   * groups of four epilogue warps pull the accumulator with tcgen05.ld (lane = box pixel), transpose it through
 //     shared memory and apply the bilinear blend + (x,y) ordering + level interleave, writing fp16 pairs
-// Roles per CTA (persistent, one per SM): warp 0 producer (coords prefetched two edges ahead), warp 1 MMA
-// issuer, warps 2.. epilogue (TC_NG groups of four); a 3-stage shared-memory ring and a TC_NG-stage TMEM ring
+// Roles per CTA (persistent, one per SM): warps 0-1 producers (alternate edges, coords prefetched two edges ahead), warp 2 MMA
+// issuer, warps 3.. epilogue (TC_NG groups of four); a 3-stage shared-memory ring and a TC_NG-stage TMEM ring
 // keep TMA, tensor pipe and epilogue overlapped.
 #include "common.cuh"
 #include <cuda.h>
 #include <cstring>
+#include <cmath>
 
 namespace dpvo {
 
@@ -36,7 +37,9 @@ constexpr int TC_STAGE_BYTES = 2 * TC_WIN0_BYTES + 2 * TC_WIN1_BYTES + 2 * TC_PA
 constexpr int TC_STAGES = 3;
 constexpr int TC_NG = 2;                       // epilogue groups == TMEM accumulator stages
 constexpr int TC_META = 16;                    // meta ring (> smem stages + accumulator stages + 1)
-constexpr int TC_THREADS = (2 + 4 * TC_NG) * 32;
+constexpr int TC_NP = 2;                       // producer warps (alternate edges; must not exceed TC_STAGES, see the kernel)
+constexpr int TC_THREADS = (TC_NP + 1 + 4 * TC_NG) * 32;
+static_assert(TC_NP <= TC_STAGES, "a producer may run at most one phase ahead of the stage it waits for");
 constexpr int TC_RAWP = 129;                   // floats per patch pixel row of the transposed accumulator
 static_assert(TC_NG == 1 || TC_NG == 2 || TC_NG == 4, "TMEM allocation must be a power of two >= 32 columns");
 static_assert(TC_STAGE_BYTES % 1024 == 0, "stages must keep the 1024 B swizzle alignment");
@@ -51,16 +54,15 @@ struct TcArgs {
   const float* coords;       // [M, 2, 3, 3]
   const int64_t* ii; const int64_t* jj;
   __half* out; int64_t out_row;
-  float div1;
+  float div1, inv1;          // inv1 = 1/div1 when div1 is a power of two (exact), else 0
   int M, H0, W0, H1, W1;
   int* fb_count; int* fb_list;   // edges whose windows do not fit the box
 };
 
-struct TcMeta {
-  float4 w[2][9];
-  int base[2][9];
-  int pitch[2];
-  int uni;
+struct __align__(16) TcMeta {   // what the producer hands to the other roles, per edge
+  int bx[2], by[2];             // box origin per level
+  int pitch[2];                 // box width per level
+  int uni;                      // 0: the edge goes to the list kernel
   int edge;
 };
 
@@ -118,6 +120,11 @@ __device__ __forceinline__ uint64_t tc_desc_sw128(uint32_t smem_addr) {
 // D fp32, A/B fp16 K-major, N = 16, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
+// level-1 coordinate: x / div (correlation is sampled at coords / 4, dpvo.py:206); a power-of-two divisor is
+// applied as an exact multiplication
+template <bool POW2> __device__ __forceinline__ float tc_level1(float x, const TcArgs& a) { return POW2 ? x * a.inv1 : x / a.div1; }
+
+template <bool POW2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 corr_fwd_tc(const __grid_constant__ TcMaps maps, const TcArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -133,7 +140,7 @@ corr_fwd_tc(const __grid_constant__ TcMaps maps, const TcArgs a) {
     for (int i = 0; i < TC_NG; ++i) { tc_mbar_init(&bars->tmem_full[i], 1); tc_mbar_init(&bars->tmem_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == TC_NP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(&bars->tmem_base)), "n"(TC_NG * 32));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
@@ -142,8 +149,11 @@ corr_fwd_tc(const __grid_constant__ TcMaps maps, const TcArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0) {
-    // ================================================================================ producer
+  if (warp < TC_NP) {
+    // ================================================================================ producers
+    // TC_NP warps take edges alternately.  Parity waits stay unambiguous because a producer that has issued
+    // edge i (stage free => MMA of edge i - STAGES retired) next waits for the stage of edge i + NP, whose
+    // previous user is edge i + NP - STAGES <= i: at most one phase behind.
     // lanes 0..17 hold the 18 coordinates of an edge, lanes 18/19 its patch / frame slot; fetched two
     // edges ahead so that the dependent global loads never sit on the critical path of the TMA issue
     auto fetch = [&](int e, float& cv, int& iv) {
@@ -155,44 +165,36 @@ corr_fwd_tc(const __grid_constant__ TcMaps maps, const TcArgs a) {
       }
     };
     float c0, c1, c2; int i0, i1, i2;
-    const int G = gridDim.x;
-    fetch(blockIdx.x, c0, i0);
-    fetch(blockIdx.x + G, c1, i1);
-    uint32_t it = 0;
-    for (int e = blockIdx.x; e < a.M; e += G, ++it) {
+    const int G = gridDim.x * TC_NP;
+    const int e_first = blockIdx.x + warp * gridDim.x;
+    fetch(e_first, c0, i0);
+    fetch(e_first + G, c1, i1);
+    uint32_t it = warp;
+    for (int e = e_first; e < a.M; e += G, it += TC_NP) {
       fetch(e + 2 * G, c2, i2);
       const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
       TcMeta& mt = meta[it % TC_META];
       const float xr = c0, yr = __shfl_down_sync(0xffffffffu, c0, 9);
       const int prow = __shfl_sync(0xffffffffu, i0, 18) * 9, slot = __shfl_sync(0xffffffffu, i0, 19);
-      // anchors / fractions of the nine patch pixels for both levels (lanes 0..8), box origin by warp min
+      // box of the nine anchors per level: one warp-wide integer min / max each (lanes 0..8 hold the pixels);
+      // the per-pixel weights are formed by the epilogue threads, off this warp's critical path
       int bx[2], by[2], bw[2], bh[2];
 #pragma unroll
       for (int lev = 0; lev < 2; ++lev) {
-        int ax = 1 << 28, ay = 1 << 28, axm = -(1 << 28), aym = -(1 << 28);
-        float fx = 0.f, fy = 0.f;
-        if (lane < 9) {
-          float x = xr, y = yr;
-          if (lev == 1) { x = x / a.div1; y = y / a.div1; }
-          ax = safe_floor_int(x) - 3; ay = safe_floor_int(y) - 3;
-          axm = ax; aym = ay;
-          fx = x - floorf(x); fy = y - floorf(y);
-        }
-        bx[lev] = warp_min_i(ax); by[lev] = warp_min_i(ay);
+        const float x = lev == 0 ? xr : tc_level1<POW2>(xr, a), y = lev == 0 ? yr : tc_level1<POW2>(yr, a);
+        const int ax = safe_floor_int(x) - 3, ay = safe_floor_int(y) - 3;
+        const bool px = lane < 9;
+        bx[lev] = __reduce_min_sync(0xffffffffu, px ? ax : (1 << 28));
+        by[lev] = __reduce_min_sync(0xffffffffu, px ? ay : (1 << 28));
         // spreads can be huge for degenerate projections: clamp before forming the box side
-        bw[lev] = min(warp_max_i(axm) - bx[lev], 64) + 8;
-        bh[lev] = min(warp_max_i(aym) - by[lev], 64) + 8;
-        if (lane < 9) {
-          mt.w[lev][lane] = make_float4((1.f - fx) * (1.f - fy), fx * (1.f - fy), (1.f - fx) * fy, fx * fy);
-          mt.base[lev][lane] = (ay - by[lev]) * bw[lev] + (ax - bx[lev]);
-        }
+        bw[lev] = min(__reduce_max_sync(0xffffffffu, px ? ax : -(1 << 28)) - bx[lev], 64) + 8;
+        bh[lev] = min(__reduce_max_sync(0xffffffffu, px ? ay : -(1 << 28)) - by[lev], 64) + 8;
       }
       const bool uni = bw[0] <= TC_L0_MAXDIM && bh[0] <= TC_L0_MAXDIM && bw[0] * bh[0] <= TC_L0_MAXROWS &&
                        bw[1] <= TC_L1_MAXDIM && bh[1] <= TC_L1_MAXDIM;
       if (lane == 0) {
-        mt.pitch[0] = bw[0]; mt.pitch[1] = bw[1];
-        mt.uni = uni ? 1 : 0;
-        mt.edge = e;
+        *reinterpret_cast<int4*>(&mt.bx[0]) = make_int4(bx[0], bx[1], by[0], by[1]);
+        *reinterpret_cast<int4*>(&mt.pitch[0]) = make_int4(bw[0], bw[1], uni ? 1 : 0, e);
         if (!uni) { const int pos = atomicAdd(a.fb_count, 1); a.fb_list[pos] = e; }
       }
       __syncwarp();
@@ -220,7 +222,7 @@ corr_fwd_tc(const __grid_constant__ TcMaps maps, const TcArgs a) {
       __syncwarp();
       c0 = c1; i0 = i1; c1 = c2; i1 = i2;
     }
-  } else if (warp == 1) {
+  } else if (warp == TC_NP) {
     // ================================================================================ MMA issuer
     uint32_t it = 0;
     for (int e = blockIdx.x; e < a.M; e += gridDim.x, ++it) {
@@ -257,8 +259,8 @@ corr_fwd_tc(const __grid_constant__ TcMaps maps, const TcArgs a) {
     // TC_NG groups of four warps take edges round-robin; a group owns one TMEM accumulator stage and one
     // transpose tile.  Thread -> (patch pixel p, taps t0 + 14k): constant for the kernel, so weights / base
     // are read once per edge.
-    const int eg = (warp - 2) >> 2;
-    const int et = (threadIdx.x - 64) & 127;
+    const int eg = (warp - TC_NP - 1) >> 2;
+    const int et = ((warp - TC_NP - 1) & 3) * 32 + lane;
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
     const int r = quarter * 32 + lane;               // box pixel owned by this thread
     const int p = et % 9, t0 = et / 9;
@@ -275,9 +277,23 @@ corr_fwd_tc(const __grid_constant__ TcMaps maps, const TcArgs a) {
       if ((int)(it % TC_NG) != eg) continue;
       const uint32_t aph = (it / TC_NG) & 1;
       const TcMeta& mt = meta[it % TC_META];
+      // this thread's patch pixel: anchor and bilinear weights per level (independent of the box, so the
+      // loads and the arithmetic overlap the wait for the accumulator)
+      const float xr = __ldg(a.coords + (int64_t)e * 18 + p), yr = __ldg(a.coords + (int64_t)e * 18 + 9 + p);
+      int ax[2], ay[2];
+      float4 w[2];
+#pragma unroll
+      for (int lev = 0; lev < 2; ++lev) {
+        const float x = lev == 0 ? xr : tc_level1<POW2>(xr, a), y = lev == 0 ? yr : tc_level1<POW2>(yr, a);
+        ax[lev] = safe_floor_int(x) - 3; ay[lev] = safe_floor_int(y) - 3;
+        const float fx = x - floorf(x), fy = y - floorf(y);
+        w[lev] = make_float4((1.f - fx) * (1.f - fy), fx * (1.f - fy), (1.f - fx) * fy, fx * fy);
+      }
       tc_mbar_wait(&bars->tmem_full[eg], aph);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      if (!mt.uni) {                                  // finished by the list kernel: just hand the stage back
+      const int4 org = *reinterpret_cast<const int4*>(&mt.bx[0]);        // bx0 bx1 by0 by1
+      const int4 shp = *reinterpret_cast<const int4*>(&mt.pitch[0]);     // pitch0 pitch1 uni edge
+      if (!shp.z) {                                   // finished by the list kernel: just hand the stage back
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         tc_mbar_arrive(&bars->tmem_empty[eg]);
         continue;
@@ -298,10 +314,10 @@ corr_fwd_tc(const __grid_constant__ TcMaps maps, const TcArgs a) {
       asm volatile("bar.sync %0, 128;\n" ::"r"(1 + eg) : "memory");
       if (et < 126) {
         __half2* orow = reinterpret_cast<__half2*>(a.out + (int64_t)e * a.out_row) + et;
-        const float4 w0 = mt.w[0][p], w1 = mt.w[1][p];
-        const int p0 = mt.pitch[0], p1 = mt.pitch[1];
-        const float* r0 = rw + p * TC_RAWP + mt.base[0][p];
-        const float* r1 = rw + (9 + p) * TC_RAWP + mt.base[1][p];
+        const int p0 = shp.x, p1 = shp.y;
+        const float* r0 = rw + p * TC_RAWP + (ay[0] - org.z) * p0 + (ax[0] - org.x);
+        const float* r1 = rw + (9 + p) * TC_RAWP + (ay[1] - org.w) * p1 + (ax[1] - org.y);
+        const float4 w0 = w[0], w1 = w[1];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (xo[k] >= 0) {
@@ -319,7 +335,7 @@ corr_fwd_tc(const __grid_constant__ TcMaps maps, const TcArgs a) {
 
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (warp == 1) {
+  if (warp == TC_NP) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TC_NG * 32));
   }
@@ -413,7 +429,11 @@ int corr_tc_forward(const void* fmap1, const int64_t* s1, int S1, const void* l0
   static bool attr = false;
   const size_t smem = corr_tc_smem_bytes();
   if (!attr) {
-    if (cudaFuncSetAttribute(corr_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return DPVO_ERR_UNSUPPORTED; }
+    if (cudaFuncSetAttribute(corr_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(corr_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return DPVO_ERR_UNSUPPORTED;
+    }
     attr = true;
   }
   int* fb = reinterpret_cast<int*>(scratch);
@@ -421,9 +441,14 @@ int corr_tc_forward(const void* fmap1, const int64_t* s1, int S1, const void* l0
   if (rc) return rc;
   TcArgs a;
   a.coords = coords; a.ii = ii; a.jj = jj; a.out = (__half*)out; a.out_row = out_row; a.div1 = div1;
+  {
+    int ex = 0;
+    a.inv1 = (std::frexp(div1, &ex) == 0.5f) ? 1.0f / div1 : 0.f;
+  }
   a.M = M; a.H0 = H0; a.W0 = W0; a.H1 = H1; a.W1 = W1; a.fb_count = fb; a.fb_list = fb + 1;
   const unsigned grid = (unsigned)std::min<int64_t>(M, sm_count());
-  corr_fwd_tc<<<grid, TC_THREADS, smem, st>>>(cache.maps, a);
+  if (a.inv1 != 0.f) corr_fwd_tc<true><<<grid, TC_THREADS, smem, st>>>(cache.maps, a);
+  else corr_fwd_tc<false><<<grid, TC_THREADS, smem, st>>>(cache.maps, a);
   DPVO_LAUNCH_CHECK("corr_fwd_tc");
   // edges whose reprojected patch is stretched beyond the box: same arithmetic on the mma.sync path
   return corr_launch_fallback_list(fmap1, s1, l0, s20, H0, W0, l1, s21, H1, W1, div1, coords, ii, jj, out, out_row, M, fb + 1, fb, st);

@@ -142,6 +142,17 @@ def test_corr_tcgen05_vs_oracle(ext, M, stretch, pad, fx, fy):
     assert bool((err <= tol).all()), float((err - tol).max())
 
 
+def test_corr_tcgen05_non_pow2_divisor(ext):
+    """level-1 divisor that is not a power of two takes the true-division instantiation"""
+    f1, l0, l1, coords, ii, jj = _pyramid_inputs(torch.half, 700, seed=5)
+    out = ext[3].corr_pyramid2(f1, l0, l1, coords, ii, jj, 3, 3.0)
+    c = coords.cpu()
+    want1 = OC.corr_forward(f1.cpu().double(), l1.cpu().double(), c / 3.0, ii.cpu(), jj.cpu(), 3)
+    err = (out[..., 1].cpu().double() - want1).abs()
+    tol = 2.0 ** -10 * want1.abs() + 1e-4 * want1.abs().max()
+    assert bool((err <= tol).all()), float((err - tol).max())
+
+
 def test_corr_tcgen05_far_outside(ext):
     """boxes entirely outside the map (also by millions of pixels) give exact zeros"""
     f1, l0, l1, coords, ii, jj = _pyramid_inputs(torch.half, 64)
