@@ -670,7 +670,7 @@ static int ba_run(BaArgs& a, int iterations, cudaStream_t st) {
     long long h[16];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    const char* names[10] = {"schur", "pair blocks", "-> cluster.sync", "sync", "dsmem reduce", "sync", "cholesky", "back-subst", "sync", "depth update"};
+    const char* names[10] = {"schur", "pair blocks", "cluster.sync", "dsmem reduce", "cluster.sync", "cholesky", "back-subst", "cluster.sync", "depth update", "cluster.sync"};
     fprintf(stderr, "[ba_solve phases, SM cycles]");
     for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%lld", names[i], h[i + 1] - h[i]);
     fprintf(stderr, " total=%lld\n", h[10] - h[0]);

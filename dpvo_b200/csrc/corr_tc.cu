@@ -128,7 +128,8 @@ template <bool POW2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 corr_fwd_tc(const __grid_constant__ TcMaps maps, const TcArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the shared array (keeps LDS/STS; an integer round trip gives generic LD/ST)
+  unsigned char* base = tc_smem_raw + ((1024u - (tc_smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   unsigned char* stages = base;                                        // [TC_STAGES][TC_STAGE_BYTES]
   float* raw = reinterpret_cast<float*>(base + TC_STAGES * TC_STAGE_BYTES);      // [TC_NG][2 lev][9][TC_RAWP]
   TcMeta* meta = reinterpret_cast<TcMeta*>(raw + TC_NG * 2 * 9 * TC_RAWP);

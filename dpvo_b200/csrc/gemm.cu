@@ -34,6 +34,7 @@ constexpr int GM_A_BYTES = GM_M * 128, GM_B_BYTES = GM_N * 128;
 constexpr int GM_TMEM_COLS = 512;
 constexpr int GM_WS_MAXKB = 6;       // weight-stationary mode: K <= 384 (6 k-blocks of the weight slice stay in smem)
 constexpr int GM_WS_ASTAGES = 4;     // activation ring depth in weight-stationary mode
+constexpr int GM_STG_FLOATS = 32 * 16; // per-warp epilogue staging tile: 32 rows x 16 columns fp32 (2 KB)
 
 struct GemmArgs {
   const __half* X; int64_t ldx;
@@ -46,6 +47,7 @@ struct GemmArgs {
   __half* Y16;                 // optional fp16 copy of the result (row stride ldy16)
   int64_t ldy16;
   int64_t rows; int N; int K; int epilogue;
+  long long* dbg;              // optional per-role timestamps of CTA 0 (DPVO_B200_GEMM_TIMING), NULL = off
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -99,6 +101,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor):
@@ -121,15 +130,22 @@ struct GemmBars {
 // life, loads that slice of W once (<= 144 KB, resident) and streams only activation tiles.  Streaming both
 // operands needs (128+192)*128 B per 128x192x64 MACs = 107 B/clk/SM at the tensor-pipe rate, 2.5x what L2
 // delivers per SM; with W resident it is 43 B/clk/SM.
+// debug timestamps: dbg[role * 16 + tile] for the first 16 tiles of CTA 0.  roles: 0 MMA tile begin, 1 MMA accumulator
+// stage free, 2 MMA tile issued, 3 epilogue accumulator ready, 4 epilogue tile done, 5 kernel begin / weights landed
+#define GM_STAMP(role, t) do { if (a.dbg && blockIdx.x == 0 && lane == 0 && (t) < 16) a.dbg[(role) * 16 + (t)] = clock64(); } while (0)
+
 template <bool GATHER, bool WS, int EPI>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
   extern __shared__ unsigned char gm_smem_raw[];
   constexpr int NST = WS ? GM_WS_ASTAGES : GM_STAGES;
-  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)gm_smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the shared array (an integer round trip would demote every
+  // access through these pointers to generic LD/ST)
+  unsigned char* base = gm_smem_raw + ((1024u - (smem_u32(gm_smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = base;
   unsigned char* sB = base + NST * GM_A_BYTES;
-  GemmBars* bars = reinterpret_cast<GemmBars*>(sB + (WS ? GM_WS_MAXKB : GM_STAGES) * GM_B_BYTES);
+  unsigned char* sStage = sB + (WS ? GM_WS_MAXKB : GM_STAGES) * GM_B_BYTES;       // [GM_EPI_WARPS][GM_STG_FLOATS] fp32
+  GemmBars* bars = reinterpret_cast<GemmBars*>(sStage + GM_EPI_WARPS * GM_STG_FLOATS * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = (a.N + GM_N - 1) / GM_N;
@@ -234,11 +250,15 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == GM_MMA_WARP) {
     // =========================================================================== MMA issuer
     uint32_t it = 0, tcount = 0;
+    GM_STAMP(5, 0);
     if constexpr (WS) mbar_wait(&bars->wfull, 0);
+    GM_STAMP(5, 1);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      GM_STAMP(0, tcount);
       mbar_wait(&bars->tmem_empty[acc], aph ^ 1);
       tc_fence_after();
+      GM_STAMP(1, tcount);
       const uint32_t d_tmem = tmem_base + acc * GM_N;
       for (int kb = 0; kb < KB; ++kb, ++it) {
         const uint32_t s = it % NST, ph = (it / NST) & 1;
@@ -255,102 +275,135 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         __syncwarp();
       }
+      GM_STAMP(2, tcount);
     }
   } else {
     // =========================================================================== epilogue
     // TMEM hands every thread one accumulator ROW (lane = row); a warp may only touch the lane quarter
     // warp % 4.  Eight warps share a tile: warps q and q+4 own the left / right 96 columns of quarter q.
-    // All element-wise work of the layer runs here, so the epilogue needs the issue slots of two
-    // warps per scheduler to keep up with the tensor pipe (4 warps were 3x slower than the MMAs).
-    // Per step: 32 columns, all loads of the step (bias, residual, gate) issued before the math.
+    // Row-per-thread global accesses cost one LSU wavefront per lane (32 rows x 16 B scattered over 32
+    // lines) and made the fused residual layers 3x slower than their MMAs, so every 32 x 16 accumulator
+    // block is transposed through a 2 KB per-warp staging tile (16-byte chunks, XOR-swizzled: conflict-free
+    // both ways) and all global traffic -- bias, residual, gate, fp32 / fp16 results -- is issued with
+    // lane = (row, 4 consecutive columns): 8 rows x 64 contiguous bytes per instruction.
     uint32_t tcount = 0;
     const int quarter = warp & 3, half = warp >> 2;
+    float4* stg = reinterpret_cast<float4*>(sStage) + warp * (GM_STG_FLOATS / 4);
+    const int lrow = lane >> 2, lc4 = lane & 3;              // this lane's row (of 8) / 4-column chunk in the write-out
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      const int64_t row = (tile / n_tiles_n) * GM_M + quarter * 32 + lane;
+      const int64_t row0 = (tile / n_tiles_n) * GM_M + quarter * 32;
       const int n0 = (int)(tile % n_tiles_n) * GM_N + half * (GM_N / 2);
-      const bool row_ok = row < a.rows;
       constexpr bool fused = (EPI == DPVO_EPI_RESADD || EPI == DPVO_EPI_GATEDRES);
-      mbar_wait(&bars->tmem_full[acc], aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GM_N + half * (GM_N / 2);
-#pragma unroll 1
-      for (int c0 = 0; c0 < GM_N / 2; c0 += 32) {
-        uint32_t r[32];
-        tc_ld32(taddr + c0, r);
-        const int col = n0 + c0;
-        const bool ok = row_ok && col < a.N;
-        float4 rv[8]; uint4 gv[4];
-        if (fused && ok) {
-          if (a.res_dtype == DPVO_F32) {
-            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res) + row * a.ldres + col);
+      constexpr int NCH = GM_N / 2 / 16;
+      // operands of the fused epilogues are fetched one 16-column chunk ahead of their use (and the first chunk
+      // before the accumulator is even ready): with one 16-byte load per lane in flight the layer ran at DRAM
+      // latency.  The residual may alias the output element for element (in-place `net += f(net)`): a thread only
+      // ever prefetches columns it has not written yet.
+      float4 rvA[4], rvB[4]; uint2 gvA[4], gvB[4];
+      auto fetch_operands = [&](int col0, float4 (&rv)[4], uint2 (&gv)[4]) {
+        if constexpr (fused) {
+          const int col = col0 + lc4 * 4;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rv[j] = rp[j];
-          } else {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.res) + row * a.ldres + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 q = rp[j];
-              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-              const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
-              rv[2 * j] = make_float4(f0.x, f0.y, f1.x, f1.y); rv[2 * j + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+          for (int it = 0; it < 4; ++it) {
+            const int64_t row = row0 + it * 8 + lrow;
+            if (row < a.rows && col0 < a.N) {
+              if (a.res_dtype == DPVO_F32) {
+                rv[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res) + row * a.ldres + col);
+              } else {
+                const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(a.res) + row * a.ldres + col);
+                rv[it] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), 0.f, 0.f);       // raw halves, unpacked at use
+              }
+              if constexpr (EPI == DPVO_EPI_GATEDRES) gv[it] = *reinterpret_cast<const uint2*>(a.gate + row * a.ldgate + col);
             }
           }
-          if constexpr (EPI == DPVO_EPI_GATEDRES) {
-            const uint4* gp = reinterpret_cast<const uint4*>(a.gate + row * a.ldgate + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) gv[j] = gp[j];
-          }
         }
-        float4 bv[8];
-        if (a.bias && col < a.N) {
-          const float4* bp = reinterpret_cast<const float4*>(a.bias + col);      // same address in every lane: broadcast
-#pragma unroll
-          for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      };
+      auto fetch_bias = [&](int col0) {
+        const int col = col0 + lc4 * 4;
+        return (a.bias && col < a.N) ? __ldg(reinterpret_cast<const float4*>(a.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      float4 bias_next = fetch_bias(n0);
+      fetch_operands(n0, rvA, gvA);
+      mbar_wait(&bars->tmem_full[acc], aph);
+      tc_fence_after();
+      GM_STAMP(3, tcount);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GM_N + half * (GM_N / 2);
+      uint32_t r[16];
+      if (n0 < a.N) tc_ld16(taddr, r);
+      // one 16-column chunk: `use` holds this chunk's operands, `pre` receives the next chunk's
+      auto chunk = [&](int c, float4 (&rv_use)[4], uint2 (&gv_use)[4], float4 (&rv_pre)[4], uint2 (&gv_pre)[4]) {
+        const int col0 = n0 + c * 16;
+        if (col0 >= a.N) return;                             // warp-uniform (N is a multiple of 32)
+        if (tcount == 1 && warp == 0 && c < 2) GM_STAMP(5, 2 + c * 4);
         tc_ld_wait();
-        if (ok) {
-          float v[32];
-          const float* bf = reinterpret_cast<const float*>(bv);
+        if (tcount == 1 && warp == 0 && c < 2) GM_STAMP(5, 3 + c * 4);
+        {                                                    // accumulator row -> staging, chunk j of row `lane`
+          const int sw = (lane >> 1) & 3;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bf[j];
-          if constexpr (fused) {
-            const float* rf = reinterpret_cast<const float*>(rv);
-            const __half* gh = reinterpret_cast<const __half*>(gv);
+          for (int j = 0; j < 4; ++j)
+            stg[lane * 4 + (j ^ sw)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        if (c + 1 < NCH && col0 + 16 < a.N) tc_ld16(taddr + (c + 1) * 16, r);
+        else { tc_fence_before(); mbar_arrive(&bars->tmem_empty[acc]); }     // last read of this accumulator stage
+        const float4 bv = bias_next;
+        if (c + 1 < NCH) { bias_next = fetch_bias(col0 + 16); fetch_operands(col0 + 16, rv_pre, gv_pre); }
+        __syncwarp();
+        const int col = col0 + lc4 * 4;
+        float4 v[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (EPI == DPVO_EPI_GATEDRES) ? rf[j] + __half2float(gh[j]) * v[j] : rf[j] + v[j];
-          } else if constexpr (EPI == DPVO_EPI_RELU) {
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + lrow;
+          v[it] = stg[rr * 4 + (lc4 ^ ((rr >> 1) & 3))];
+        }
+        __syncwarp();                                        // staging tile free for the next chunk
+        if (tcount == 1 && warp == 0 && c < 2) GM_STAMP(5, 4 + c * 4);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if constexpr (EPI == DPVO_EPI_SIGMOID) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
-          }
-          uint4 o[4];
-          __half2* hh = reinterpret_cast<__half2*>(o);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) hh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-          if (a.y_dtype == DPVO_F16) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.Y) + row * a.ldy + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = o[j];
-          } else {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + row * a.ldy + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (a.Y16) {
-            uint4* dst = reinterpret_cast<uint4*>(a.Y16 + row * a.ldy16 + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = o[j];
+        for (int it = 0; it < 4; ++it) {
+          const int64_t row = row0 + it * 8 + lrow;
+          if (row < a.rows) {
+            float4 o4 = v[it];
+            o4.x += bv.x; o4.y += bv.y; o4.z += bv.z; o4.w += bv.w;
+            if constexpr (fused) {
+              float4 rr4 = rv_use[it];
+              if (a.res_dtype != DPVO_F32) {
+                const uint32_t q0 = __float_as_uint(rr4.x), q1 = __float_as_uint(rr4.y);
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&q1));
+                rr4 = make_float4(f0.x, f0.y, f1.x, f1.y);
+              }
+              if constexpr (EPI == DPVO_EPI_GATEDRES) {
+                const uint2 q = gv_use[it];
+                const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+                o4.x = rr4.x + g0.x * o4.x; o4.y = rr4.y + g0.y * o4.y; o4.z = rr4.z + g1.x * o4.z; o4.w = rr4.w + g1.y * o4.w;
+              } else {
+                o4.x += rr4.x; o4.y += rr4.y; o4.z += rr4.z; o4.w += rr4.w;
+              }
+            } else if constexpr (EPI == DPVO_EPI_RELU) {
+              o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f);
+            } else if constexpr (EPI == DPVO_EPI_SIGMOID) {
+              o4.x = __fdividef(1.0f, 1.0f + __expf(-o4.x)); o4.y = __fdividef(1.0f, 1.0f + __expf(-o4.y));
+              o4.z = __fdividef(1.0f, 1.0f + __expf(-o4.z)); o4.w = __fdividef(1.0f, 1.0f + __expf(-o4.w));
+            }
+            uint2 o;
+            *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(o4.x, o4.y);
+            *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(o4.z, o4.w);
+            if (a.y_dtype == DPVO_F16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.Y) + row * a.ldy + col) = o;
+            else *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + row * a.ldy + col) = o4;
+            if (a.Y16) *reinterpret_cast<uint2*>(a.Y16 + row * a.ldy16 + col) = o;
           }
         }
+      };
+      static_assert(NCH % 2 == 0, "chunks are processed in pairs (two operand buffers)");
+      // (timing build: slots 5/2.. hold, for warp 0 on its second tile, chunk begin / accumulator in registers / transposed,
+      //  for chunks 0 and 1)
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        chunk(c, rvA, gvA, rvB, gvB);
+        chunk(c + 1, rvB, gvB, rvA, gvA);
       }
-      tc_fence_before();
-      mbar_arrive(&bars->tmem_empty[acc]);
+      GM_STAMP(4, tcount);
+      if (n0 >= a.N) { tc_fence_before(); mbar_arrive(&bars->tmem_empty[acc]); }
     }
   }
 
@@ -399,7 +452,7 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
 template <bool GATHER, bool WS, int EPI>
 static int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, unsigned grid, cudaStream_t st) {
   const size_t smem = (WS ? (size_t)GM_WS_ASTAGES * GM_A_BYTES + (size_t)GM_WS_MAXKB * GM_B_BYTES
-                          : (size_t)GM_STAGES * (GM_A_BYTES + GM_B_BYTES)) + sizeof(GemmBars) + 1024;
+                          : (size_t)GM_STAGES * (GM_A_BYTES + GM_B_BYTES)) + (size_t)GM_EPI_WARPS * GM_STG_FLOATS * 4 + sizeof(GemmBars) + 1024;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(linear_f16_kernel<GATHER, WS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -457,8 +510,11 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
   DPVO_REQUIRE(epilogue >= DPVO_EPI_NONE && epilogue <= DPVO_EPI_GATEDRES, "linear_f16: unknown epilogue %d", epilogue);
   if (epilogue == DPVO_EPI_RESADD || epilogue == DPVO_EPI_GATEDRES)
     DPVO_REQUIRE(res && (res_dtype == DPVO_F16 || res_dtype == DPVO_F32), "linear_f16: residual operand missing");
-  if (epilogue == DPVO_EPI_GATEDRES) DPVO_REQUIRE(gate && ldgate % 2 == 0, "linear_f16: gate operand missing or odd stride");
-  DPVO_REQUIRE(!res || ldres % 2 == 0, "linear_f16: residual row stride must be even");
+  if (epilogue == DPVO_EPI_GATEDRES)
+    DPVO_REQUIRE(gate && ldgate % 4 == 0 && ((uintptr_t)gate & 7) == 0, "linear_f16: gate operand missing, or rows not 8-byte aligned");
+  DPVO_REQUIRE(!res || (ldres % 4 == 0 && ((uintptr_t)res & (res_dtype == DPVO_F32 ? 15 : 7)) == 0),
+               "linear_f16: residual rows must be aligned to 4 elements");
+  DPVO_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "linear_f16: bias must be 16-byte aligned");
   GemmArgs a;
   a.X = (const __half*)X; a.ldx = ldx; a.W = (const __half*)W; a.ldw = ldw; a.bias = bias; a.gather = gather;
   a.res = res; a.res_dtype = res_dtype; a.ldres = ldres; a.gate = (const __half*)gate; a.ldgate = ldgate;
@@ -466,5 +522,23 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
   a.Y16 = (__half*)Y16; a.ldy16 = ldy16;
   a.Y = Y; a.y_dtype = y_dtype; a.ldy = ldy; a.rows = rows; a.N = N; a.K = K; a.epilogue = epilogue;
 
-  return linear_launch(a, (cudaStream_t)stream);
+  static long long* dbg = nullptr;
+  const bool timing = getenv("DPVO_B200_GEMM_TIMING") != nullptr;
+  if (timing && !dbg) cudaMalloc(&dbg, 96 * sizeof(long long));
+  a.dbg = timing ? dbg : nullptr;
+  if (timing) cudaMemsetAsync(dbg, 0, 96 * sizeof(long long), (cudaStream_t)stream);
+  const int rc = linear_launch(a, (cudaStream_t)stream);
+  if (timing && rc == DPVO_OK) {
+    long long h[96];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[5 * 16];
+    fprintf(stderr, "[linear_f16 CTA 0, SM cycles from kernel begin] rows=%lld N=%d K=%d epi=%d  weights landed %lld\n", (long long)rows, N, K, epilogue, h[5 * 16 + 1] - t0);
+    for (int t = 0; t < 16 && h[t]; ++t)
+      fprintf(stderr, "   tile %d: mma begin %lld  acc free %lld  issued %lld | epi ready %lld  done %lld\n", t, h[t] - t0, h[16 + t] - t0,
+              h[32 + t] - t0, h[48 + t] - t0, h[64 + t] - t0);
+    fprintf(stderr, "   warp 0, tile 1: chunk0 begin %lld  acc in regs %lld  transposed %lld | chunk1 begin %lld  acc in regs %lld  transposed %lld\n",
+            h[82] - t0, h[83] - t0, h[84] - t0, h[86] - t0, h[87] - t0, h[88] - t0);
+  }
+  return rc;
 }
