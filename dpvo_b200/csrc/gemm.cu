@@ -34,6 +34,7 @@ constexpr int GM_A_BYTES = GM_M * 128, GM_B_BYTES = GM_N * 128;
 constexpr int GM_TMEM_COLS = 512;
 constexpr int GM_WS_MAXKB = 6;       // weight-stationary mode: K <= 384 (6 k-blocks of the weight slice stay in smem)
 constexpr int GM_WS_ASTAGES = 4;     // activation ring depth in weight-stationary mode
+constexpr int GM_OUT_F16 = 0, GM_OUT_F32 = 1, GM_OUT_F32_F16 = 2;   // result: fp16 | fp32 | fp32 plus an fp16 copy
 constexpr int GM_STG_FLOATS = 32 * 16; // per-warp epilogue staging tile: 32 rows x 16 columns fp32 (2 KB)
 
 struct GemmArgs {
@@ -47,6 +48,7 @@ struct GemmArgs {
   __half* Y16;                 // optional fp16 copy of the result (row stride ldy16)
   int64_t ldy16;
   int64_t rows; int N; int K; int epilogue;
+  int prefetch;                // residual / gate tensor maps are valid: prefetch their tiles into L2
   long long* dbg;              // optional per-role timestamps of CTA 0 (DPVO_B200_GEMM_TIMING), NULL = off
 };
 
@@ -78,6 +80,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
                "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
+}
+// L2 prefetch of a 2-D tile (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -134,9 +140,10 @@ struct GemmBars {
 // stage free, 2 MMA tile issued, 3 epilogue accumulator ready, 4 epilogue tile done, 5 kernel begin / weights landed
 #define GM_STAMP(role, t) do { if (a.dbg && blockIdx.x == 0 && lane == 0 && (t) < 16) a.dbg[(role) * 16 + (t)] = clock64(); } while (0)
 
-template <bool GATHER, bool WS, int EPI>
+template <bool GATHER, bool WS, int EPI, int OUT>
 __global__ void __launch_bounds__(GM_THREADS, 1)
-linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
+linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmG, const GemmArgs a) {
   extern __shared__ unsigned char gm_smem_raw[];
   constexpr int NST = WS ? GM_WS_ASTAGES : GM_STAGES;
   // 1024-byte alignment by pointer arithmetic on the shared array (an integer round trip would demote every
@@ -168,6 +175,17 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
+  // The residual / gate tiles the epilogue of a tile will read are pulled into L2 while its MMAs run: the fp32
+  // state (73 MB) plus its fp16 copies do not fit L2, and at DRAM latency the epilogue's few loads in flight
+  // per lane bounded the fused layers at ~1.8 TB/s.
+  auto prefetch_epilogue_operands = [&](int m0, int n0) {
+    if constexpr (EPI == DPVO_EPI_RESADD || EPI == DPVO_EPI_GATEDRES) {
+      if (a.prefetch) {
+        tma_prefetch_l2_2d(&tmR, n0, m0);
+        if constexpr (EPI == DPVO_EPI_GATEDRES) tma_prefetch_l2_2d(&tmG, n0, m0);
+      }
+    }
+  };
   if (warp > GM_MMA_WARP) {
     // =========================================================================== producers
     if constexpr (!GATHER) {
@@ -181,6 +199,7 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
           const int m0 = (int)((tile / n_tiles_n) * GM_M);
           const int n0 = (int)(tile % n_tiles_n) * GM_N;
+          prefetch_epilogue_operands(m0, n0);
           for (int kb = 0; kb < KB; ++kb, ++it) {
             const uint32_t s = it % NST, ph = (it / NST) & 1;
             mbar_wait(&bars->empty[s], ph ^ 1);
@@ -204,6 +223,7 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t m0 = (tile / n_tiles_n) * GM_M;
         const int n0 = (int)(tile % n_tiles_n) * GM_N;
+        if (pt == 0) prefetch_epilogue_operands((int)m0, n0);
         const __half* arow[8]; uint32_t aoff[8], abytes[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -290,54 +310,61 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quarter = warp & 3, half = warp >> 2;
     float4* stg = reinterpret_cast<float4*>(sStage) + warp * (GM_STG_FLOATS / 4);
     const int lrow = lane >> 2, lc4 = lane & 3;              // this lane's row (of 8) / 4-column chunk in the write-out
+    constexpr bool fused = (EPI == DPVO_EPI_RESADD || EPI == DPVO_EPI_GATEDRES);
+    constexpr int NCH = GM_N / 2 / 16;
+    // Everything below is written so that one chunk is straight-line code (no branches on dtypes / optional outputs /
+    // row bounds inside it): its four 8-row steps are independent and only then does the compiler interleave them --
+    // with two epilogue warps per scheduler the dependent-issue latency of serialised steps was the whole cost.
+    constexpr int YB = (OUT == GM_OUT_F16) ? 2 : 4;          // bytes per element of Y
+    const int64_t ystep = 8 * a.ldy * YB, y16step = 8 * a.ldy16 * 2;     // byte strides between the 8-row steps
+    const int64_t rstep = 8 * a.ldres * (a.res_dtype == DPVO_F32 ? 4 : 2), gstep = 8 * a.ldgate * 2;
+    const bool res32 = a.res_dtype == DPVO_F32;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      const int64_t row0 = (tile / n_tiles_n) * GM_M + quarter * 32;
+      const int64_t row0 = (tile / n_tiles_n) * GM_M + quarter * 32 + lrow;   // this lane's row in step 0
       const int n0 = (int)(tile % n_tiles_n) * GM_N + half * (GM_N / 2);
-      constexpr bool fused = (EPI == DPVO_EPI_RESADD || EPI == DPVO_EPI_GATEDRES);
-      constexpr int NCH = GM_N / 2 / 16;
+      const int nch = min(NCH, max(0, (a.N - n0) / 16));     // valid chunks (N is a multiple of 32)
+      bool ok[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) ok[it] = row0 + it * 8 < a.rows;
+      const int colL = n0 + lc4 * 4;                          // this lane's first column in chunk 0
+      char* yp = reinterpret_cast<char*>(a.Y) + (row0 * a.ldy + colL) * YB;
+      char* y16p = reinterpret_cast<char*>(a.Y16) + (row0 * a.ldy16 + colL) * 2;
+      const char* rp = reinterpret_cast<const char*>(a.res) + (row0 * a.ldres + colL) * (res32 ? 4 : 2);
+      const char* gp = reinterpret_cast<const char*>(a.gate) + (row0 * a.ldgate + colL) * 2;
+      const float* bp = a.bias ? a.bias + colL : nullptr;
       // operands of the fused epilogues are fetched one 16-column chunk ahead of their use (and the first chunk
       // before the accumulator is even ready): with one 16-byte load per lane in flight the layer ran at DRAM
       // latency.  The residual may alias the output element for element (in-place `net += f(net)`): a thread only
       // ever prefetches columns it has not written yet.
       float4 rvA[4], rvB[4]; uint2 gvA[4], gvB[4];
-      auto fetch_operands = [&](int col0, float4 (&rv)[4], uint2 (&gv)[4]) {
+      auto fetch_operands = [&](int c, float4 (&rv)[4], uint2 (&gv)[4]) {
         if constexpr (fused) {
-          const int col = col0 + lc4 * 4;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            const int64_t row = row0 + it * 8 + lrow;
-            if (row < a.rows && col0 < a.N) {
-              if (a.res_dtype == DPVO_F32) {
-                rv[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res) + row * a.ldres + col);
-              } else {
-                const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(a.res) + row * a.ldres + col);
-                rv[it] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), 0.f, 0.f);       // raw halves, unpacked at use
-              }
-              if constexpr (EPI == DPVO_EPI_GATEDRES) gv[it] = *reinterpret_cast<const uint2*>(a.gate + row * a.ldgate + col);
+            if (ok[it] && c < nch) {
+              const char* p = rp + it * rstep + c * (res32 ? 64 : 32);
+              if (res32) rv[it] = *reinterpret_cast<const float4*>(p);
+              else { const uint2 q = *reinterpret_cast<const uint2*>(p); rv[it] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), 0.f, 0.f); }
+              if constexpr (EPI == DPVO_EPI_GATEDRES) gv[it] = *reinterpret_cast<const uint2*>(gp + it * gstep + c * 32);
             }
           }
         }
       };
-      auto fetch_bias = [&](int col0) {
-        const int col = col0 + lc4 * 4;
-        return (a.bias && col < a.N) ? __ldg(reinterpret_cast<const float4*>(a.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      float4 bias_next = fetch_bias(n0);
-      fetch_operands(n0, rvA, gvA);
+      auto fetch_bias = [&](int c) { return (bp && c < nch) ? __ldg(reinterpret_cast<const float4*>(bp + c * 16)) : make_float4(0.f, 0.f, 0.f, 0.f); };
+      float4 bias_next = fetch_bias(0);
+      fetch_operands(0, rvA, gvA);
       mbar_wait(&bars->tmem_full[acc], aph);
       tc_fence_after();
       GM_STAMP(3, tcount);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GM_N + half * (GM_N / 2);
       uint32_t r[16];
-      if (n0 < a.N) tc_ld16(taddr, r);
+      if (nch > 0) tc_ld16(taddr, r);
+      else { tc_fence_before(); mbar_arrive(&bars->tmem_empty[acc]); }
       // one 16-column chunk: `use` holds this chunk's operands, `pre` receives the next chunk's
       auto chunk = [&](int c, float4 (&rv_use)[4], uint2 (&gv_use)[4], float4 (&rv_pre)[4], uint2 (&gv_pre)[4]) {
-        const int col0 = n0 + c * 16;
-        if (col0 >= a.N) return;                             // warp-uniform (N is a multiple of 32)
-        if (tcount == 1 && warp == 0 && c < 2) GM_STAMP(5, 2 + c * 4);
+        if (c >= nch) return;                                // warp-uniform
         tc_ld_wait();
-        if (tcount == 1 && warp == 0 && c < 2) GM_STAMP(5, 3 + c * 4);
         {                                                    // accumulator row -> staging, chunk j of row `lane`
           const int sw = (lane >> 1) & 3;
 #pragma unroll
@@ -345,12 +372,12 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             stg[lane * 4 + (j ^ sw)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                    __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         }
-        if (c + 1 < NCH && col0 + 16 < a.N) tc_ld16(taddr + (c + 1) * 16, r);
+        if (c + 1 < nch) tc_ld16(taddr + (c + 1) * 16, r);
         else { tc_fence_before(); mbar_arrive(&bars->tmem_empty[acc]); }     // last read of this accumulator stage
         const float4 bv = bias_next;
-        if (c + 1 < NCH) { bias_next = fetch_bias(col0 + 16); fetch_operands(col0 + 16, rv_pre, gv_pre); }
+        bias_next = fetch_bias(c + 1);
+        fetch_operands(c + 1, rv_pre, gv_pre);
         __syncwarp();
-        const int col = col0 + lc4 * 4;
         float4 v[4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -358,52 +385,47 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           v[it] = stg[rr * 4 + (lc4 ^ ((rr >> 1) & 3))];
         }
         __syncwarp();                                        // staging tile free for the next chunk
-        if (tcount == 1 && warp == 0 && c < 2) GM_STAMP(5, 4 + c * 4);
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const int64_t row = row0 + it * 8 + lrow;
-          if (row < a.rows) {
-            float4 o4 = v[it];
-            o4.x += bv.x; o4.y += bv.y; o4.z += bv.z; o4.w += bv.w;
-            if constexpr (fused) {
-              float4 rr4 = rv_use[it];
-              if (a.res_dtype != DPVO_F32) {
-                const uint32_t q0 = __float_as_uint(rr4.x), q1 = __float_as_uint(rr4.y);
-                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&q1));
-                rr4 = make_float4(f0.x, f0.y, f1.x, f1.y);
-              }
-              if constexpr (EPI == DPVO_EPI_GATEDRES) {
-                const uint2 q = gv_use[it];
-                const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-                o4.x = rr4.x + g0.x * o4.x; o4.y = rr4.y + g0.y * o4.y; o4.z = rr4.z + g1.x * o4.z; o4.w = rr4.w + g1.y * o4.w;
-              } else {
-                o4.x += rr4.x; o4.y += rr4.y; o4.z += rr4.z; o4.w += rr4.w;
-              }
-            } else if constexpr (EPI == DPVO_EPI_RELU) {
-              o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f);
-            } else if constexpr (EPI == DPVO_EPI_SIGMOID) {
-              o4.x = __fdividef(1.0f, 1.0f + __expf(-o4.x)); o4.y = __fdividef(1.0f, 1.0f + __expf(-o4.y));
-              o4.z = __fdividef(1.0f, 1.0f + __expf(-o4.z)); o4.w = __fdividef(1.0f, 1.0f + __expf(-o4.w));
+          float4 o4 = v[it];
+          o4.x += bv.x; o4.y += bv.y; o4.z += bv.z; o4.w += bv.w;
+          if constexpr (fused) {
+            float4 rr4 = rv_use[it];
+            {
+              const uint32_t q0 = __float_as_uint(rr4.x), q1 = __float_as_uint(rr4.y);
+              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&q1));
+              rr4 = res32 ? rr4 : make_float4(f0.x, f0.y, f1.x, f1.y);
             }
-            uint2 o;
-            *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(o4.x, o4.y);
-            *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(o4.z, o4.w);
-            if (a.y_dtype == DPVO_F16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.Y) + row * a.ldy + col) = o;
-            else *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + row * a.ldy + col) = o4;
-            if (a.Y16) *reinterpret_cast<uint2*>(a.Y16 + row * a.ldy16 + col) = o;
+            if constexpr (EPI == DPVO_EPI_GATEDRES) {
+              const uint2 q = gv_use[it];
+              const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+              o4.x = rr4.x + g0.x * o4.x; o4.y = rr4.y + g0.y * o4.y; o4.z = rr4.z + g1.x * o4.z; o4.w = rr4.w + g1.y * o4.w;
+            } else {
+              o4.x += rr4.x; o4.y += rr4.y; o4.z += rr4.z; o4.w += rr4.w;
+            }
+          } else if constexpr (EPI == DPVO_EPI_RELU) {
+            o4.x = fmaxf(o4.x, 0.f); o4.y = fmaxf(o4.y, 0.f); o4.z = fmaxf(o4.z, 0.f); o4.w = fmaxf(o4.w, 0.f);
+          } else if constexpr (EPI == DPVO_EPI_SIGMOID) {
+            o4.x = __fdividef(1.0f, 1.0f + __expf(-o4.x)); o4.y = __fdividef(1.0f, 1.0f + __expf(-o4.y));
+            o4.z = __fdividef(1.0f, 1.0f + __expf(-o4.z)); o4.w = __fdividef(1.0f, 1.0f + __expf(-o4.w));
+          }
+          uint2 o;
+          *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(o4.x, o4.y);
+          *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(o4.z, o4.w);
+          if (ok[it]) {
+            if constexpr (OUT == GM_OUT_F16) *reinterpret_cast<uint2*>(yp + it * ystep + c * 32) = o;
+            else *reinterpret_cast<float4*>(yp + it * ystep + c * 64) = o4;
+            if constexpr (OUT == GM_OUT_F32_F16) *reinterpret_cast<uint2*>(y16p + it * y16step + c * 32) = o;
           }
         }
       };
       static_assert(NCH % 2 == 0, "chunks are processed in pairs (two operand buffers)");
-      // (timing build: slots 5/2.. hold, for warp 0 on its second tile, chunk begin / accumulator in registers / transposed,
-      //  for chunks 0 and 1)
 #pragma unroll 1
       for (int c = 0; c < NCH; c += 2) {
         chunk(c, rvA, gvA, rvB, gvB);
         chunk(c + 1, rvB, gvB, rvA, gvA);
       }
       GM_STAMP(4, tcount);
-      if (n0 >= a.N) { tc_fence_before(); mbar_arrive(&bars->tmem_empty[acc]); }
     }
   }
 
@@ -449,47 +471,74 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
   return DPVO_OK;
 }
 
-template <bool GATHER, bool WS, int EPI>
-static int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, unsigned grid, cudaStream_t st) {
+template <bool GATHER, bool WS, int EPI, int OUT>
+static int launch_out(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmG, const GemmArgs& a, unsigned grid, cudaStream_t st) {
   const size_t smem = (WS ? (size_t)GM_WS_ASTAGES * GM_A_BYTES + (size_t)GM_WS_MAXKB * GM_B_BYTES
                           : (size_t)GM_STAGES * (GM_A_BYTES + GM_B_BYTES)) + (size_t)GM_EPI_WARPS * GM_STG_FLOATS * 4 + sizeof(GemmBars) + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(linear_f16_kernel<GATHER, WS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(linear_f16_kernel<GATHER, WS, EPI, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "linear_f16: cudaFuncSetAttribute");
     attr = true;
   }
-  linear_f16_kernel<GATHER, WS, EPI><<<grid, GM_THREADS, smem, st>>>(tmA, tmB, a);
+  linear_f16_kernel<GATHER, WS, EPI, OUT><<<grid, GM_THREADS, smem, st>>>(tmA, tmB, tmR, tmG, a);
   DPVO_LAUNCH_CHECK("linear_f16_kernel");
   return DPVO_OK;
 }
 
+template <bool GATHER, bool WS, int EPI>
+static int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmG, const GemmArgs& a, unsigned grid, cudaStream_t st) {
+  if (a.y_dtype == DPVO_F16) return launch_out<GATHER, WS, EPI, GM_OUT_F16>(tmA, tmB, tmR, tmG, a, grid, st);
+  if (a.Y16) return launch_out<GATHER, WS, EPI, GM_OUT_F32_F16>(tmA, tmB, tmR, tmG, a, grid, st);
+  return launch_out<GATHER, WS, EPI, GM_OUT_F32>(tmA, tmB, tmR, tmG, a, grid, st);
+}
+
 template <bool GATHER, bool WS>
-static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, unsigned grid, cudaStream_t st) {
+static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmG, const GemmArgs& a, unsigned grid, cudaStream_t st) {
   switch (a.epilogue) {
-    case DPVO_EPI_NONE: return launch_epi<GATHER, WS, DPVO_EPI_NONE>(tmA, tmB, a, grid, st);
-    case DPVO_EPI_RELU: return launch_epi<GATHER, WS, DPVO_EPI_RELU>(tmA, tmB, a, grid, st);
-    case DPVO_EPI_SIGMOID: return launch_epi<GATHER, WS, DPVO_EPI_SIGMOID>(tmA, tmB, a, grid, st);
-    case DPVO_EPI_RESADD: return launch_epi<GATHER, WS, DPVO_EPI_RESADD>(tmA, tmB, a, grid, st);
-    default: return launch_epi<GATHER, WS, DPVO_EPI_GATEDRES>(tmA, tmB, a, grid, st);
+    case DPVO_EPI_NONE: return launch_epi<GATHER, WS, DPVO_EPI_NONE>(tmA, tmB, tmR, tmG, a, grid, st);
+    case DPVO_EPI_RELU: return launch_epi<GATHER, WS, DPVO_EPI_RELU>(tmA, tmB, tmR, tmG, a, grid, st);
+    case DPVO_EPI_SIGMOID: return launch_epi<GATHER, WS, DPVO_EPI_SIGMOID>(tmA, tmB, tmR, tmG, a, grid, st);
+    case DPVO_EPI_RESADD: return launch_epi<GATHER, WS, DPVO_EPI_RESADD>(tmA, tmB, tmR, tmG, a, grid, st);
+    default: return launch_epi<GATHER, WS, DPVO_EPI_GATEDRES>(tmA, tmB, tmR, tmG, a, grid, st);
   }
 }
 
-static int linear_launch(const GemmArgs& a, cudaStream_t st) {
+// plain (unswizzled) 2-D map over an epilogue operand, used only for L2 prefetches of GM_M x GM_N tiles
+static bool make_prefetch_tmap(CUtensorMap* m, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_tiled();
+  const int es = dtype == DPVO_F32 ? 4 : 2;
+  if (!fn || ((uintptr_t)ptr & 15) || (ld * es) % 16) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)std::min<int64_t>(cols, GM_N), (cuuint32_t)GM_M};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, dtype == DPVO_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int linear_launch(GemmArgs& a, cudaStream_t st) {
   const int n_tiles_n = (a.N + GM_N - 1) / GM_N;
   const int64_t tiles = ((a.rows + GM_M - 1) / GM_M) * n_tiles_n;
   const bool ws = (a.K / GM_K) <= GM_WS_MAXKB && !getenv("DPVO_B200_GEMM_STREAM");
   // weight-stationary CTAs keep their column slice: the grid must be a multiple of the slice count
   int64_t grid = std::min<int64_t>(tiles, sm_count());
   if (ws) grid = std::max<int64_t>(n_tiles_n, grid / n_tiles_n * n_tiles_n);
-  CUtensorMap tmA, tmB;
-  memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
+  CUtensorMap tmA, tmB, tmR, tmG;
+  memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB)); memset(&tmR, 0, sizeof(tmR)); memset(&tmG, 0, sizeof(tmG));
   int rc = make_tmap(&tmB, a.W, a.N, a.K, a.ldw, GM_N);
   if (rc) return rc;
-  if (a.gather) return ws ? launch_variant<true, true>(tmA, tmB, a, (unsigned)grid, st) : launch_variant<true, false>(tmA, tmB, a, (unsigned)grid, st);
+  a.prefetch = 0;
+  if ((a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES) && !getenv("DPVO_B200_GEMM_NOPREFETCH")) {
+    bool ok = make_prefetch_tmap(&tmR, a.res, a.res_dtype, a.rows, a.N, a.ldres);
+    if (ok && a.epilogue == DPVO_EPI_GATEDRES) ok = make_prefetch_tmap(&tmG, a.gate, DPVO_F16, a.rows, a.N, a.ldgate);
+    a.prefetch = ok ? 1 : 0;
+  }
+  if (a.gather) return ws ? launch_variant<true, true>(tmA, tmB, tmR, tmG, a, (unsigned)grid, st) : launch_variant<true, false>(tmA, tmB, tmR, tmG, a, (unsigned)grid, st);
   rc = make_tmap(&tmA, a.X, a.rows, a.K, a.ldx, GM_M);
   if (rc) return rc;
-  return ws ? launch_variant<false, true>(tmA, tmB, a, (unsigned)grid, st) : launch_variant<false, false>(tmA, tmB, a, (unsigned)grid, st);
+  return ws ? launch_variant<false, true>(tmA, tmB, tmR, tmG, a, (unsigned)grid, st) : launch_variant<false, false>(tmA, tmB, tmR, tmG, a, (unsigned)grid, st);
 }
 
 extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather, const void* W, int64_t ldw,
@@ -519,6 +568,7 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
   a.X = (const __half*)X; a.ldx = ldx; a.W = (const __half*)W; a.ldw = ldw; a.bias = bias; a.gather = gather;
   a.res = res; a.res_dtype = res_dtype; a.ldres = ldres; a.gate = (const __half*)gate; a.ldgate = ldgate;
   DPVO_REQUIRE(!Y16 || (ldy16 % 8 == 0 && ((uintptr_t)Y16 & 15) == 0), "linear_f16: Y16 rows must be 16-byte aligned");
+  DPVO_REQUIRE(!Y16 || y_dtype == DPVO_F32, "linear_f16: the fp16 copy accompanies an fp32 result (an fp16 result needs none)");
   a.Y16 = (__half*)Y16; a.ldy16 = ldy16;
   a.Y = Y; a.y_dtype = y_dtype; a.ldy = ldy; a.rows = rows; a.N = N; a.K = K; a.epilogue = epilogue;
 
@@ -537,8 +587,6 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
     for (int t = 0; t < 16 && h[t]; ++t)
       fprintf(stderr, "   tile %d: mma begin %lld  acc free %lld  issued %lld | epi ready %lld  done %lld\n", t, h[t] - t0, h[16 + t] - t0,
               h[32 + t] - t0, h[48 + t] - t0, h[64 + t] - t0);
-    fprintf(stderr, "   warp 0, tile 1: chunk0 begin %lld  acc in regs %lld  transposed %lld | chunk1 begin %lld  acc in regs %lld  transposed %lld\n",
-            h[82] - t0, h[83] - t0, h[84] - t0, h[86] - t0, h[87] - t0, h[88] - t0);
   }
   return rc;
 }
