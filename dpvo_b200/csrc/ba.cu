@@ -311,15 +311,17 @@ ba_reduce_kernel(const BaArgs a) {
 // ==========================================================================================
 constexpr int BA_LD = 6 * BA_MAX_N + 1;       // leading dimension (odd: conflict-free columns); row N6 = rhs
 constexpr int BA_REC_CHUNK = 64;              // pair records staged per round
+constexpr int BA_ELD = 6 * BA_MAX_N + 4;      // row pitch of the staged E rows [E_k | u_k | 0..]: a multiple of 4, rows load as float4
+constexpr int BA_ECH = 32;                    // patches per Schur chunk
 
 struct SolveSmem {
   float S[BA_LD][BA_LD];                      // upper triangle while accumulating, lower triangle for the factor
   float dx[6 * BA_MAX_N];
-  union {
-    float Et[32][BA_LD];                      // tile of E rows (Schur phase)
+  float inv_diag[6 * BA_MAX_N];               // 1 / L_kk, kept by the factorisation for the back substitution
+  union alignas(16) {
+    float Et[2][BA_ECH][BA_ELD];              // double-buffered tiles of augmented E rows (Schur phase)
     float recs[BA_REC_CHUNK][BA_REC];         // pair records (assembly phase)
   };
-  float Qt[32], Ut[32];
   int rec_i[BA_REC_CHUNK], rec_j[BA_REC_CHUNK];
 };
 
@@ -349,39 +351,103 @@ ba_solve_kernel(const BaArgs a) {
   if (N > 0) {
     for (int o = tid; o < (N6 + 1) * N6; o += BA_SOLVE_THREADS) sm.S[o / N6][o % N6] = 0.0f;
     __syncthreads();
-    // ---- 1a. Schur products over this CTA's patches
-    const int H = N6 / 2, n_micro = H * (H + 1) / 2;
-    for (int mbase = m0; mbase < m1; mbase += 32) {
-      const int cnt = min(32, m1 - mbase);
-      for (int i = tid; i < cnt * N6; i += BA_SOLVE_THREADS) {
-        const int r = i / N6, c = i - r * N6;
-        sm.Et[r][c] = a.Ed[(int64_t)(mbase + r) * N6 + c];
-      }
-      if (tid < cnt) { sm.Qt[tid] = a.Qk[mbase + tid]; sm.Ut[tid] = a.uk[mbase + tid]; }
-      __syncthreads();
-      for (int mt = tid; mt < n_micro + N6; mt += BA_SOLVE_THREADS) {
-        if (mt < n_micro) {
-          int r2 = 0, rem = mt;
-          while (rem >= H - r2) { rem -= H - r2; ++r2; }
-          const int c2 = r2 + rem;
-          float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
-          for (int k = 0; k < cnt; ++k) {
-            const float q = sm.Qt[k];
-            const float e0 = q * sm.Et[k][2 * r2], e1 = q * sm.Et[k][2 * r2 + 1];
-            const float f0 = sm.Et[k][2 * c2], f1 = sm.Et[k][2 * c2 + 1];
-            a00 += e0 * f0; a01 += e0 * f1; a10 += e1 * f0; a11 += e1 * f1;
-          }
-          sm.S[2 * r2][2 * c2] -= a00; sm.S[2 * r2][2 * c2 + 1] -= a01;
-          sm.S[2 * r2 + 1][2 * c2 + 1] -= a11;
-          if (r2 != c2) sm.S[2 * r2 + 1][2 * c2] -= a10;
-        } else {
-          const int row = mt - n_micro;
-          float s = 0.0f;
-          for (int k = 0; k < cnt; ++k) s += sm.Qt[k] * sm.Ut[k] * sm.Et[k][row];
-          sm.S[N6][row] -= s;
+    // ---- 1a. Schur products over this CTA's patches.  Rows are staged as sqrt(Q_k) [E_k | u_k | 0..]: the gradient
+    // term - sum_k Q_k u_k E_k becomes one more column of the same register-tiled product.  4x4 tiles (two 16-byte
+    // shared loads per 16 FMAs -- with 2x2 tiles the phase was bound by shared-memory bandwidth), the rows of a
+    // chunk split over up to three thread groups per tile, and the next chunk in flight in registers meanwhile.
+    // Warp w stages rows w and w+16 of a chunk, lanes stride the columns: no integer division in the loop.
+    const int NA = (N6 + 4) & ~3, H = NA / 4, n_tiles4 = H * (H + 1) / 2;
+    const int n_chunks = (m1 - m0 + BA_ECH - 1) / BA_ECH;
+    constexpr int NWARP = BA_SOLVE_THREADS / 32;
+    constexpr int RPW = BA_ECH / NWARP;                                  // rows per warp and chunk
+    constexpr int CPL = (BA_ELD + 31) / 32;                              // columns per lane
+    static_assert(BA_ECH % NWARP == 0, "chunk rows divide over the warps");
+    float pre[RPW][CPL], preq[RPW];
+    auto fetch_chunk = [&](int ch) {                         // loads only: nothing here waits for them
+      const int mbase = m0 + ch * BA_ECH;
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        const int g = mbase + warp + rr * NWARP;
+        const bool on = g < m1;
+        preq[rr] = on ? a.Qk[g] : 0.f;                                    // rows past the slice add nothing
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) {
+          const int c = lane + 32 * u;
+          float v = 0.f;
+          if (on && c < N6) v = a.Ed[(int64_t)g * N6 + c];
+          else if (on && c == N6) v = a.uk[g];
+          pre[rr][u] = v;
         }
       }
+    };
+    auto store_chunk = [&](int buf) {
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        const float sq = sqrtf(preq[rr]);
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) {
+          const int c = lane + 32 * u;
+          if (c < NA) sm.Et[buf][warp + rr * NWARP][c] = sq * pre[rr][u];
+        }
+      }
+    };
+    // work item of this thread: tile (r4 <= c4) and k-split; constant over the chunks
+    const int ksplit = max(1, min(3, BA_SOLVE_THREADS / n_tiles4));
+    const int rounds = (n_tiles4 * ksplit + BA_SOLVE_THREADS - 1) / BA_SOLVE_THREADS;   // 1 unless > 16 free poses
+    BA_STAMP(11);
+    if (n_chunks > 0) { fetch_chunk(0); store_chunk(0); }
+    __syncthreads();
+    BA_STAMP(12);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int buf = ch & 1;
+      if (ch + 1 < n_chunks) fetch_chunk(ch + 1);
+      if (ch == 1) BA_STAMP(13);
+      for (int rd = 0; rd < rounds; ++rd) {
+        const int item = tid + rd * BA_SOLVE_THREADS;
+        const int sp = item / n_tiles4, mt = item - sp * n_tiles4;
+        const bool live = sp < ksplit;
+        int r4 = 0, c4 = 0;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        if (live) {
+          int rem = mt;
+          while (rem >= H - r4) { rem -= H - r4; ++r4; }
+          c4 = r4 + rem;
+          const int kper = (BA_ECH + ksplit - 1) / ksplit;
+          const int kb = sp * kper, ke = min(BA_ECH, kb + kper);
+#pragma unroll 4
+          for (int k = kb; k < ke; ++k) {
+            const float4 e = *reinterpret_cast<const float4*>(&sm.Et[buf][k][4 * r4]);
+            const float4 f = *reinterpret_cast<const float4*>(&sm.Et[buf][k][4 * c4]);
+            const float ev[4] = {e.x, e.y, e.z, e.w}, fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] += ev[i] * fv[j];
+          }
+        }
+        // the k-splits of a tile add into S one after the other (fixed order)
+        for (int ph = 0; ph < ksplit; ++ph) {
+          if (live && sp == ph) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int row = 4 * r4 + i, col = 4 * c4 + j;
+                if (col < N6) { if (row <= col) sm.S[row][col] -= acc[i][j]; }
+                else if (col == N6 && row < N6) sm.S[N6][row] -= acc[i][j];     // augmented column = gradient row
+              }
+          }
+          if (ksplit > 1 || rounds > 1) __syncthreads();
+        }
+      }
+      if (ch == 1) BA_STAMP(14);
+      if (ch + 1 < n_chunks) store_chunk(buf ^ 1);
       __syncthreads();
+      if (ch == 1) BA_STAMP(15);
     }
     BA_STAMP(1);
     // ---- 1b. pose blocks from this CTA's share of the pair records (pairs rank, rank+8, ...)
@@ -400,39 +466,34 @@ ba_solve_kernel(const BaArgs a) {
         sm.rec_j[tid] = (fj >= 0 && fj < N) ? (int)fj : -1;
       }
       __syncthreads();
-      if (tid < 96) {
-        // targets of one record are distinct; records are applied one after the other (fixed order)
+      if (tid < 63) {
+        // Every entry of S is owned by ONE thread for all records (diagonal blocks: thread (x,y) serves both the
+        // source-pose and the target-pose block; off-diagonal blocks are stored for the ordered pose pair, the
+        // thread takes the transposed element when the record runs the other way), so records need no barrier
+        // between them and are applied in index order by each owner.
+        int x = 0, y = 0;
+        if (tid < 21) { int rem = tid; while (rem >= 6 - x) { rem -= 6 - x; ++x; } y = x + rem; }
+        else if (tid < 57) { const int e = tid - 21; x = e / 6; y = e - 6 * x; }
         for (int r = 0; r < cn; ++r) {
           const int bi = sm.rec_i[r], bj = sm.rec_j[r];
           const float* rc = sm.recs[r];
-          if (tid < 21) {                                  // J_i J_i^T  -> block (i,i), upper triangle
+          if (tid < 21) {                                    // upper triangles of J_i J_i^T -> (i,i) and J_j J_j^T -> (j,j)
             if (bi >= 0) {
-              int x = 0, rem = tid;
-              while (rem >= 6 - x) { rem -= 6 - x; ++x; }
-              const int y = x + rem;
               float v = rc[tid];
               if (bi == bj) v += rc[57 + tid] + rc[21 + x * 6 + y] + rc[21 + y * 6 + x];   // self edge i -> i
               sm.S[6 * bi + x][6 * bi + y] += v;
             }
-          } else if (tid < 42) {                           // J_j J_j^T  -> block (j,j)
-            if (bj >= 0 && bi != bj) {
-              const int e = tid - 21;
-              int x = 0, rem = e;
-              while (rem >= 6 - x) { rem -= 6 - x; ++x; }
-              sm.S[6 * bj + x][6 * bj + x + rem] += rc[57 + e];
-            }
-          } else if (tid < 78) {                           // -J_i J_j^T -> block (i,j) or its transpose
+            if (bj >= 0 && bi != bj) sm.S[6 * bj + x][6 * bj + y] += rc[57 + tid];
+          } else if (tid < 57) {                             // -J_i J_j^T -> block (min, max)
             if (bi >= 0 && bj >= 0 && bi != bj) {
-              const int e = tid - 42, x = e / 6, y = e - 6 * x;
-              if (bi < bj) sm.S[6 * bi + x][6 * bj + y] += rc[21 + e];
-              else sm.S[6 * bj + y][6 * bi + x] += rc[21 + e];
+              if (bi < bj) sm.S[6 * bi + x][6 * bj + y] += rc[21 + x * 6 + y];
+              else sm.S[6 * bj + x][6 * bi + y] += rc[21 + y * 6 + x];
             }
-          } else if (tid < 84) {                           // gradient, pose i (and j for a self edge)
-            if (bi >= 0) sm.S[N6][6 * bi + tid - 78] += rc[tid] + ((bi == bj) ? rc[tid + 6] : 0.0f);
-          } else if (tid < 90) {                           // gradient, pose j
-            if (bj >= 0 && bi != bj) sm.S[N6][6 * bj + tid - 84] += rc[tid];
+          } else {                                           // gradient of pose i and pose j
+            const int c = tid - 57;
+            if (bi >= 0) sm.S[N6][6 * bi + c] += rc[78 + c] + ((bi == bj) ? rc[84 + c] : 0.0f);
+            if (bj >= 0 && bi != bj) sm.S[N6][6 * bj + c] += rc[84 + c];
           }
-          asm volatile("bar.sync 1, 96;\n" ::: "memory");
         }
       }
       __syncthreads();
@@ -459,57 +520,108 @@ ba_solve_kernel(const BaArgs a) {
   BA_STAMP(5);
 
   if (N > 0 && rank == 0) {
-    // ---- 3. blocked Cholesky of [S; y^T] (lower storage, row N6 = rhs): 6-column panels
+    // ---- 3. blocked Cholesky of [S; y^T] (lower storage, row N6 = rhs): 6-column panels.
+    // Per panel: (a) one thread factors the 6x6 diagonal block and inverts the factor entirely in registers (the
+    // shared-memory version spent > 3000 cycles per panel in dependent loads); (b) the rows below become
+    // A_ik L_kk^-T, 21 independent FMAs per row, no divisions; (c) the trailing update runs on a (16 x 32) thread
+    // grid -- a warp shares row i (broadcast loads), lanes stride j <= i -- with no integer division.
+    float* linv = &sm.Et[0][0][0];                         // 21 entries of L_kk^-1 (row-major lower), free E-tile area
     for (int kb = 0; kb < N; ++kb) {
       const int k0 = 6 * kb;
-      if (tid == 0) {                                    // factor the 6x6 diagonal block
+      if (tid == 0) {
+        float A[6][6], Li[6][6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) A[r][c] = sm.S[k0 + r][k0 + c];
+#pragma unroll
         for (int c = 0; c < 6; ++c) {
-          float d = sm.S[k0 + c][k0 + c];
-          for (int l = 0; l < c; ++l) d -= sm.S[k0 + c][k0 + l] * sm.S[k0 + c][k0 + l];
+          float d = A[c][c];
+#pragma unroll
+          for (int l = 0; l < c; ++l) d -= A[c][l] * A[c][l];
           d = sqrtf(d);
-          sm.S[k0 + c][k0 + c] = d;
+          const float id = 1.0f / d;
+          A[c][c] = d;
+          Li[c][c] = id;
+#pragma unroll
           for (int r = c + 1; r < 6; ++r) {
-            float v = sm.S[k0 + r][k0 + c];
-            for (int l = 0; l < c; ++l) v -= sm.S[k0 + r][k0 + l] * sm.S[k0 + c][k0 + l];
-            sm.S[k0 + r][k0 + c] = v / d;
+            float v = A[r][c];
+#pragma unroll
+            for (int l = 0; l < c; ++l) v -= A[r][l] * A[c][l];
+            A[r][c] = v * id;
           }
+        }
+        // inverse of the lower-triangular factor, column by column
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+#pragma unroll
+          for (int r = c + 1; r < 6; ++r) {
+            float v = 0.f;
+#pragma unroll
+            for (int l = c; l < r; ++l) v -= A[r][l] * Li[l][c];
+            Li[r][c] = v * Li[r][r];
+          }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          sm.inv_diag[k0 + r] = Li[r][r];
+#pragma unroll
+          for (int c = 0; c <= r; ++c) { sm.S[k0 + r][k0 + c] = A[r][c]; linv[r * (r + 1) / 2 + c] = Li[r][c]; }
         }
       }
       __syncthreads();
       for (int i = k0 + 6 + tid; i <= N6; i += BA_SOLVE_THREADS) {     // panel: rows below (+ rhs row)
-        float v[6];
+        float av[6], v[6];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          float t = sm.S[i][k0 + c];
+        for (int c = 0; c < 6; ++c) av[c] = sm.S[i][k0 + c];
 #pragma unroll
-          for (int l = 0; l < 6; ++l) if (l < c) t -= v[l] * sm.S[k0 + c][k0 + l];
-          v[c] = t / sm.S[k0 + c][k0 + c];
+        for (int c = 0; c < 6; ++c) {                                  // (A L^-T)[c] = sum_{l <= c} A[l] Linv[c][l]
+          float t = 0.f;
+#pragma unroll
+          for (int l = 0; l <= c; ++l) t += av[l] * linv[c * (c + 1) / 2 + l];
+          v[c] = t;
         }
 #pragma unroll
         for (int c = 0; c < 6; ++c) sm.S[i][k0 + c] = v[c];
       }
       __syncthreads();
-      const int rem = N6 - k0 - 6;                                      // trailing rows (without rhs)
-      for (int o = tid; o < (rem + 1) * rem; o += BA_SOLVE_THREADS) {
-        const int i = k0 + 6 + o / rem, j = k0 + 6 + o % rem;          // i may be the rhs row N6
-        if (j <= i) {
+      for (int i = k0 + 6 + warp; i <= N6; i += BA_SOLVE_THREADS / 32) {   // trailing rows (i = N6: the rhs row)
+        float li[6];
+#pragma unroll
+        for (int l = 0; l < 6; ++l) li[l] = sm.S[i][k0 + l];
+        const int jend = min(i, N6 - 1);
+        for (int j = k0 + 6 + lane; j <= jend; j += 32) {
           float t = 0.0f;
 #pragma unroll
-          for (int l = 0; l < 6; ++l) t += sm.S[i][k0 + l] * sm.S[j][k0 + l];
+          for (int l = 0; l < 6; ++l) t += li[l] * sm.S[j][k0 + l];
           sm.S[i][j] -= t;
         }
       }
       __syncthreads();
     }
     BA_STAMP(6);
-    // row N6 now holds z = L^-1 y; back substitution L^T x = z with one warp
+    // row N6 now holds z = L^-1 y; back substitution L^T x = z with one warp, z kept in registers
+    // (lane l owns entries l, l+32, ...): per step one row of L from shared memory, one shuffle, no stores
     if (tid < 32) {
-      for (int k = N6 - 1; k >= 0; --k) {
-        float xk = 0.0f;
-        if (tid == (k & 31)) { xk = sm.S[N6][k] / sm.S[k][k]; sm.dx[k] = xk; }
-        xk = __shfl_sync(0xffffffffu, xk, k & 31);
-        for (int i = tid; i < k; i += 32) sm.S[N6][i] -= sm.S[k][i] * xk;
-        __syncwarp();
+      constexpr int ZR = (6 * BA_MAX_N + 31) / 32;
+      float z[ZR];
+#pragma unroll
+      for (int u = 0; u < ZR; ++u) z[u] = (lane + 32 * u < N6) ? sm.S[N6][lane + 32 * u] : 0.0f;
+#pragma unroll
+      for (int uk = ZR - 1; uk >= 0; --uk) {                // segment of 32 unknowns whose z lives in z[uk]
+        if (32 * uk >= N6) continue;
+        for (int kk = min(31, N6 - 1 - 32 * uk); kk >= 0; --kk) {
+          const int k = 32 * uk + kk;
+          // (1/d) z_k instead of z_k / d: the factor is stored with its reciprocal diagonal
+          const float xk = __shfl_sync(0xffffffffu, z[uk], kk) * sm.inv_diag[k];
+          if (lane == kk) sm.dx[k] = xk;
+#pragma unroll
+          for (int u = 0; u < ZR; ++u) {
+            if (u <= uk) {
+              const int i = lane + 32 * u;
+              if (i < k) z[u] -= sm.S[k][i] * xk;
+            }
+          }
+        }
       }
     }
     __syncthreads();
@@ -520,27 +632,53 @@ ba_solve_kernel(const BaArgs a) {
   BA_STAMP(8);
 
   // ---- 4. depth back-substitution dZ = Q (u - E^T dX) and patch retraction (ba_cuda.cu:209-229)
-  float* dxs = sm.Qt;      // reuse: per-CTA copy of dX needs N6 <= 192 floats -> use the Et area instead
-  dxs = &sm.Et[0][0];
+  float* dxs = &sm.Et[0][0][0];      // per-CTA copy of dX (N6 <= 192 floats) in the free E-tile area
   if (N > 0) {
     const SolveSmem* root = cluster.map_shared_rank(&sm, 0);
     for (int i = tid; i < N6; i += BA_SOLVE_THREADS) dxs[i] = root->dx[i];
   }
   __syncthreads();
-  for (int g = m0 + warp; g < m1; g += BA_SOLVE_THREADS / 32) {
-    float dot = 0.0f;
-    if (N > 0) {
-      const float* er = a.Ed + (int64_t)g * N6;
-      for (int k = lane; k < N6; k += 32) dot += er[k] * dxs[k];
-      dot = warp_sum(dot);
+  {
+    // a warp's patches: their E rows, Q, u and current depths are all requested before any is used (the loop
+    // used to expose one global-memory latency per patch)
+    constexpr int NW = BA_SOLVE_THREADS / 32;
+    constexpr int DB = 4;                                  // patches per batch and warp
+    constexpr int ER = (6 * BA_MAX_N + 31) / 32;
+    for (int g0 = m0 + warp; g0 < m1; g0 += NW * DB) {
+      float er[DB][ER], qk[DB], uk[DB], d0[DB];
+      float* pd[DB];
+#pragma unroll
+      for (int b = 0; b < DB; ++b) {
+        const int g = g0 + b * NW;
+        const bool on = g < m1;
+#pragma unroll
+        for (int u = 0; u < ER; ++u) {
+          const int k = lane + 32 * u;
+          er[b][u] = (on && k < N6) ? a.Ed[(int64_t)g * N6 + k] : 0.0f;
+        }
+        qk[b] = on ? a.Qk[g] : 0.0f;
+        uk[b] = on ? a.uk[g] : 0.0f;
+        pd[b] = on ? a.patches + (a.k_key[g] * 3 + 2) * P * P : nullptr;
+        d0[b] = on ? pd[b][0] : 0.0f;
+      }
+#pragma unroll
+      for (int b = 0; b < DB; ++b) {
+        float dot = 0.0f;
+#pragma unroll
+        for (int u = 0; u < ER; ++u) {
+          const int k = lane + 32 * u;
+          if (k < N6) dot += er[b][u] * dxs[k];
+        }
+        dot = warp_sum(dot);
+        if (pd[b]) {
+          const float dz = qk[b] * (uk[b] - dot);
+          float d = d0[b] + dz;
+          d = (d > 20.0f) ? 1.0f : d;
+          d = fmaxf(d, 1e-4f);
+          if (lane < P * P) pd[b][lane] = d;
+        }
+      }
     }
-    const float dz = a.Qk[g] * (a.uk[g] - dot);
-    float* pd = a.patches + (a.k_key[g] * 3 + 2) * P * P;
-    float d = pd[0] + dz;
-    d = (d > 20.0f) ? 1.0f : d;
-    d = fmaxf(d, 1e-4f);
-    __syncwarp();
-    if (lane < P * P) pd[lane] = d;
   }
   BA_STAMP(9);
   // ---- 5. pose retraction (ba_cuda.cu:178-206), after every CTA is done reading dx
@@ -673,7 +811,8 @@ static int ba_run(BaArgs& a, int iterations, cudaStream_t st) {
     const char* names[10] = {"schur", "pair blocks", "cluster.sync", "dsmem reduce", "cluster.sync", "cholesky", "back-subst", "cluster.sync", "depth update", "cluster.sync"};
     fprintf(stderr, "[ba_solve phases, SM cycles]");
     for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%lld", names[i], h[i + 1] - h[i]);
-    fprintf(stderr, " total=%lld\n", h[10] - h[0]);
+    fprintf(stderr, " total=%lld | schur detail: setup %lld, first chunk staged %lld, chunk 1: multiply %lld, stage next + barrier %lld\n", h[10] - h[0],
+            h[11] - h[0], h[12] - h[11], h[14] - h[13], h[15] - h[14]);
   }
   return DPVO_OK;
 }
