@@ -391,63 +391,65 @@ ba_solve_kernel(const BaArgs a) {
         }
       }
     };
-    // work item of this thread: tile (r4 <= c4) and k-split; constant over the chunks
+    // work item of a thread: tile (r4 <= c4) and k-split, constant over the chunks, so the 4x4 accumulator stays
+    // in registers for the whole slice and S is touched once at the end (rounds > 1 only beyond 16 free poses;
+    // the slice is then staged once per round)
     const int ksplit = max(1, min(3, BA_SOLVE_THREADS / n_tiles4));
-    const int rounds = (n_tiles4 * ksplit + BA_SOLVE_THREADS - 1) / BA_SOLVE_THREADS;   // 1 unless > 16 free poses
-    BA_STAMP(11);
-    if (n_chunks > 0) { fetch_chunk(0); store_chunk(0); }
-    __syncthreads();
-    BA_STAMP(12);
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int buf = ch & 1;
-      if (ch + 1 < n_chunks) fetch_chunk(ch + 1);
-      if (ch == 1) BA_STAMP(13);
-      for (int rd = 0; rd < rounds; ++rd) {
-        const int item = tid + rd * BA_SOLVE_THREADS;
-        const int sp = item / n_tiles4, mt = item - sp * n_tiles4;
-        const bool live = sp < ksplit;
-        int r4 = 0, c4 = 0;
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        if (live) {
-          int rem = mt;
-          while (rem >= H - r4) { rem -= H - r4; ++r4; }
-          c4 = r4 + rem;
-          const int kper = (BA_ECH + ksplit - 1) / ksplit;
-          const int kb = sp * kper, ke = min(BA_ECH, kb + kper);
-#pragma unroll 4
-          for (int k = kb; k < ke; ++k) {
-            const float4 e = *reinterpret_cast<const float4*>(&sm.Et[buf][k][4 * r4]);
-            const float4 f = *reinterpret_cast<const float4*>(&sm.Et[buf][k][4 * c4]);
-            const float ev[4] = {e.x, e.y, e.z, e.w}, fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) acc[i][j] += ev[i] * fv[j];
-          }
-        }
-        // the k-splits of a tile add into S one after the other (fixed order)
-        for (int ph = 0; ph < ksplit; ++ph) {
-          if (live && sp == ph) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int row = 4 * r4 + i, col = 4 * c4 + j;
-                if (col < N6) { if (row <= col) sm.S[row][col] -= acc[i][j]; }
-                else if (col == N6 && row < N6) sm.S[N6][row] -= acc[i][j];     // augmented column = gradient row
-              }
-          }
-          if (ksplit > 1 || rounds > 1) __syncthreads();
-        }
+    const int rounds = (n_tiles4 * ksplit + BA_SOLVE_THREADS - 1) / BA_SOLVE_THREADS;
+    const int kper = (BA_ECH + ksplit - 1) / ksplit;
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int item = tid + rd * BA_SOLVE_THREADS;
+      const int sp = item / n_tiles4, mt = item - sp * n_tiles4;
+      const bool live = sp < ksplit;
+      int r4 = 0, c4 = 0;
+      if (live) {
+        int rem = mt;
+        while (rem >= H - r4) { rem -= H - r4; ++r4; }
+        c4 = r4 + rem;
       }
-      if (ch == 1) BA_STAMP(14);
-      if (ch + 1 < n_chunks) store_chunk(buf ^ 1);
+      const int kb = sp * kper, ke = live ? min(BA_ECH, kb + kper) : kb;
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      if (rd == 0) BA_STAMP(11);
+      if (n_chunks > 0) { fetch_chunk(0); store_chunk(0); }
       __syncthreads();
-      if (ch == 1) BA_STAMP(15);
+      if (rd == 0) BA_STAMP(12);
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < n_chunks) fetch_chunk(ch + 1);
+        if (ch == 1) BA_STAMP(13);
+#pragma unroll 4
+        for (int k = kb; k < ke; ++k) {
+          const float4 e = *reinterpret_cast<const float4*>(&sm.Et[buf][k][4 * r4]);
+          const float4 f = *reinterpret_cast<const float4*>(&sm.Et[buf][k][4 * c4]);
+          const float ev[4] = {e.x, e.y, e.z, e.w}, fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += ev[i] * fv[j];
+        }
+        if (ch == 1) BA_STAMP(14);
+        if (ch + 1 < n_chunks) store_chunk(buf ^ 1);
+        __syncthreads();
+        if (ch == 1) BA_STAMP(15);
+      }
+      // the k-splits of a tile add into S one after the other (fixed order)
+      for (int ph = 0; ph < ksplit; ++ph) {
+        if (live && sp == ph) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int row = 4 * r4 + i, col = 4 * c4 + j;
+              if (col < N6) { if (row <= col) sm.S[row][col] -= acc[i][j]; }
+              else if (col == N6 && row < N6) sm.S[N6][row] -= acc[i][j];     // augmented column = gradient row
+            }
+        }
+        __syncthreads();
+      }
     }
     BA_STAMP(1);
     // ---- 1b. pose blocks from this CTA's share of the pair records (pairs rank, rank+8, ...)
@@ -639,45 +641,59 @@ ba_solve_kernel(const BaArgs a) {
   }
   __syncthreads();
   {
-    // a warp's patches: their E rows, Q, u and current depths are all requested before any is used (the loop
-    // used to expose one global-memory latency per patch)
+    // Scalars of a patch (key, Q, u, current depth) are fetched one THREAD per patch -- two dependent global
+    // latencies for the whole slice instead of per patch --, the dot products E_k . dX one WARP per patch with the
+    // rows of eight patches in flight, the new depth is written back thread per patch.
     constexpr int NW = BA_SOLVE_THREADS / 32;
-    constexpr int DB = 4;                                  // patches per batch and warp
+    constexpr int DB = 8;
     constexpr int ER = (6 * BA_MAX_N + 31) / 32;
-    for (int g0 = m0 + warp; g0 < m1; g0 += NW * DB) {
-      float er[DB][ER], qk[DB], uk[DB], d0[DB];
-      float* pd[DB];
-#pragma unroll
-      for (int b = 0; b < DB; ++b) {
-        const int g = g0 + b * NW;
-        const bool on = g < m1;
-#pragma unroll
-        for (int u = 0; u < ER; ++u) {
-          const int k = lane + 32 * u;
-          er[b][u] = (on && k < N6) ? a.Ed[(int64_t)g * N6 + k] : 0.0f;
-        }
-        qk[b] = on ? a.Qk[g] : 0.0f;
-        uk[b] = on ? a.uk[g] : 0.0f;
-        pd[b] = on ? a.patches + (a.k_key[g] * 3 + 2) * P * P : nullptr;
-        d0[b] = on ? pd[b][0] : 0.0f;
+    float* sc_q = dxs + 6 * BA_MAX_N;                      // [BA_SOLVE_THREADS] each, in the free E-tile area
+    float* sc_u = sc_q + BA_SOLVE_THREADS;
+    float* sc_dot = sc_u + BA_SOLVE_THREADS;
+    for (int base = m0; base < m1; base += BA_SOLVE_THREADS) {
+      const int cnt = min(BA_SOLVE_THREADS, m1 - base);
+      float* pd = nullptr;
+      float d0 = 0.f;
+      if (tid < cnt) {
+        const int g = base + tid;
+        sc_q[tid] = a.Qk[g];
+        sc_u[tid] = a.uk[g];
+        pd = a.patches + (a.k_key[g] * 3 + 2) * P * P;
+        d0 = pd[0];
       }
+      for (int q0 = warp; q0 < cnt; q0 += NW * DB) {
+        float er[DB][ER];
 #pragma unroll
-      for (int b = 0; b < DB; ++b) {
-        float dot = 0.0f;
+        for (int b = 0; b < DB; ++b) {
+          const int q = q0 + b * NW;
 #pragma unroll
-        for (int u = 0; u < ER; ++u) {
-          const int k = lane + 32 * u;
-          if (k < N6) dot += er[b][u] * dxs[k];
+          for (int u = 0; u < ER; ++u) {
+            const int k = lane + 32 * u;
+            er[b][u] = (q < cnt && k < N6) ? a.Ed[(int64_t)(base + q) * N6 + k] : 0.0f;
+          }
         }
-        dot = warp_sum(dot);
-        if (pd[b]) {
-          const float dz = qk[b] * (uk[b] - dot);
-          float d = d0[b] + dz;
-          d = (d > 20.0f) ? 1.0f : d;
-          d = fmaxf(d, 1e-4f);
-          if (lane < P * P) pd[b][lane] = d;
+#pragma unroll
+        for (int b = 0; b < DB; ++b) {
+          const int q = q0 + b * NW;
+          float dot = 0.0f;
+#pragma unroll
+          for (int u = 0; u < ER; ++u) {
+            const int k = lane + 32 * u;
+            if (k < N6) dot += er[b][u] * dxs[k];
+          }
+          dot = warp_sum(dot);
+          if (lane == 0 && q < cnt) sc_dot[q] = dot;
         }
       }
+      __syncthreads();
+      if (tid < cnt) {
+        const float dz = sc_q[tid] * (sc_u[tid] - sc_dot[tid]);
+        float d = d0 + dz;
+        d = (d > 20.0f) ? 1.0f : d;
+        d = fmaxf(d, 1e-4f);
+        for (int i = 0; i < P * P; ++i) pd[i] = d;
+      }
+      __syncthreads();
     }
   }
   BA_STAMP(9);

@@ -37,52 +37,76 @@ constexpr int ROW_WARPS = 8;
 constexpr int MAX_V4 = 8;     // up to 8 float4 per lane -> dim <= 1024
 
 // ---- add + LayerNorm ------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+// NV = float4 per lane (dim = 128 NV, 3 for the update operator); a warp normalises RPW rows at a time so that
+// the loads of all of them are in flight before the first reduction (one row per warp and 70 registers left
+// the kernel at a third of the HBM rate: too few bytes in flight per SM).
+template <int NV, int RPW>
+__global__ void __launch_bounds__(ROW_WARPS * 32, (NV * RPW <= 6) ? 3 : 2)
 add_layernorm_kernel(const void* a, const void* b, const void* c, int da, int db, int dc,
                      const int64_t* __restrict__ b_index,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      float* y32, __half* y16, int relu, int64_t rows, int dim) {
   const int lane = threadIdx.x & 31;
-  const int nv = dim >> 7;    // float4 per lane (dim % 128 == 0)
-  for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * ROW_WARPS) {
-    float4 v[MAX_V4];
-    float s = 0.f;
-    const int64_t rb = b_index ? b_index[r] : r;      // operand b may be gathered (ctx = imap[kk], dpvo.py:334)
+  const int64_t wstride = (int64_t)gridDim.x * ROW_WARPS * RPW;
+  for (int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5)) * RPW; r0 < rows; r0 += wstride) {
+    float4 v[RPW][NV];
 #pragma unroll
-    for (int i = 0; i < MAX_V4; ++i) {
-      if (i < nv) {
-        const int64_t e = r * dim + (i * 32 + lane) * 4;
-        float4 t = load4(a, da, e);
-        if (b) t = add4(t, load4(b, db, rb * dim + (i * 32 + lane) * 4));
-        if (c) t = add4(t, load4(c, dc, e));
-        v[i] = t;
-        s += (t.x + t.y) + (t.z + t.w);
+    for (int k = 0; k < RPW; ++k) {
+      const int64_t r = r0 + k;
+      const bool on = r < rows;
+      const int64_t rb = (on && b_index) ? b_index[r] : r;      // operand b may be gathered (ctx = imap[kk], dpvo.py:334)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
+          const int64_t e = r * dim + (i * 32 + lane) * 4;
+          t = load4(a, da, e);
+          if (b) t = add4(t, load4(b, db, rb * dim + (i * 32 + lane) * 4));
+          if (c) t = add4(t, load4(c, dc, e));
+        }
+        v[k][i] = t;
       }
     }
-    const float mean = warp_sum(s) / (float)dim;
-    float q = 0.f;
+    float mean[RPW], rstd[RPW];
 #pragma unroll
-    for (int i = 0; i < MAX_V4; ++i) {
-      if (i < nv) {
-        const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    for (int k = 0; k < RPW; ++k) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s += (v[k][i].x + v[k][i].y) + (v[k][i].z + v[k][i].w);
+      mean[k] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < RPW; ++k) mean[k] = warp_sum(mean[k]) / (float)dim;
+#pragma unroll
+    for (int k = 0; k < RPW; ++k) {
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float dx = v[k][i].x - mean[k], dy = v[k][i].y - mean[k], dz = v[k][i].z - mean[k], dw = v[k][i].w - mean[k];
         q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
       }
+      rstd[k] = q;
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)dim + eps);
 #pragma unroll
-    for (int i = 0; i < MAX_V4; ++i) {
-      if (i < nv) {
-        const int col = (i * 32 + lane) * 4;
-        const float4 g = *reinterpret_cast<const float4*>(gamma + col);
-        const float4 bt = *reinterpret_cast<const float4*>(beta + col);
-        float4 o;
-        o.x = (v[i].x - mean) * rstd * g.x + bt.x;
-        o.y = (v[i].y - mean) * rstd * g.y + bt.y;
-        o.z = (v[i].z - mean) * rstd * g.z + bt.z;
-        o.w = (v[i].w - mean) * rstd * g.w + bt.w;
-        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (y32) store4(y32, DPVO_F32, r * dim + col, o);
-        if (y16) store4(y16, DPVO_F16, r * dim + col, o);
+    for (int k = 0; k < RPW; ++k) rstd[k] = rsqrtf(warp_sum(rstd[k]) / (float)dim + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + col);
+#pragma unroll
+      for (int k = 0; k < RPW; ++k) {
+        const int64_t r = r0 + k;
+        if (r < rows) {
+          float4 o;
+          o.x = (v[k][i].x - mean[k]) * rstd[k] * g.x + bt.x;
+          o.y = (v[k][i].y - mean[k]) * rstd[k] * g.y + bt.y;
+          o.z = (v[k][i].z - mean[k]) * rstd[k] * g.z + bt.z;
+          o.w = (v[k][i].w - mean[k]) * rstd[k] * g.w + bt.w;
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (y32) store4(y32, DPVO_F32, r * dim + col, o);
+          if (y16) store4(y16, DPVO_F16, r * dim + col, o);
+        }
       }
     }
   }
@@ -135,25 +159,40 @@ gated_residual_kernel(const float* x, const __half* g, const __half* res, float*
 }
 
 // ---- SoftAgg: one CTA per group, one thread per 2 channels, single pass online softmax --------
+// The rows of a group are scattered (order[]), so each step is a dependent global load; four rows are
+// requested before the first is consumed (the 74-edge (i,j) groups ran at one memory latency per edge).
 __global__ void __launch_bounds__(256)
 softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ gl, int64_t ld,
                       const int32_t* __restrict__ order,
                       const int32_t* __restrict__ group_start, const int32_t* __restrict__ n_groups,
                       __half* __restrict__ y, int dim) {
+  constexpr int PF = 4;
   const int G = *n_groups;
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int s = group_start[g], e = group_start[g + 1];
     for (int col = threadIdx.x * 2; col < dim; col += blockDim.x * 2) {
       float m0 = -INFINITY, m1 = -INFINITY, z0 = 0.f, z1 = 0.f, a0 = 0.f, a1 = 0.f;
-      for (int k = s; k < e; ++k) {
-        const int64_t row = (int64_t)order[k] * ld + col;
-        const float2 gv = __half22float2(*reinterpret_cast<const __half2*>(gl + row));
-        const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(f + row));
-        if (gv.x > m0) { const float sc = __expf(m0 - gv.x); z0 *= sc; a0 *= sc; m0 = gv.x; }
-        if (gv.y > m1) { const float sc = __expf(m1 - gv.y); z1 *= sc; a1 *= sc; m1 = gv.y; }
-        const float w0 = __expf(gv.x - m0), w1 = __expf(gv.y - m1);
-        z0 += w0; a0 += w0 * fv.x;
-        z1 += w1; a1 += w1 * fv.y;
+      for (int k0 = s; k0 < e; k0 += PF) {
+        __half2 gq[PF], fq[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+          if (k0 + u < e) {
+            const int64_t row = (int64_t)order[k0 + u] * ld + col;
+            gq[u] = *reinterpret_cast<const __half2*>(gl + row);
+            fq[u] = *reinterpret_cast<const __half2*>(f + row);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+          if (k0 + u < e) {
+            const float2 gv = __half22float2(gq[u]), fv = __half22float2(fq[u]);
+            if (gv.x > m0) { const float sc = __expf(m0 - gv.x); z0 *= sc; a0 *= sc; m0 = gv.x; }
+            if (gv.y > m1) { const float sc = __expf(m1 - gv.y); z1 *= sc; a1 *= sc; m1 = gv.y; }
+            const float w0 = __expf(gv.x - m0), w1 = __expf(gv.y - m1);
+            z0 += w0; a0 += w0 * fv.x;
+            z1 += w1; a1 += w1 * fv.y;
+          }
+        }
       }
       *reinterpret_cast<__half2*>(y + (int64_t)g * dim + col) = __floats2half2_rn(a0 / z0, a1 / z1);
     }
@@ -211,9 +250,24 @@ extern "C" int dpvo_add_layernorm(const void* a, const void* b, const void* c, c
   DPVO_REQUIRE(a && in_dtypes && gamma && beta && (y32 || y16), "add_layernorm: null pointer");
   DPVO_REQUIRE(dim % 128 == 0 && dim <= 128 * MAX_V4, "add_layernorm: dim must be a multiple of 128, <= %d", 128 * MAX_V4);
   DPVO_REQUIRE(ok_dt(in_dtypes[0]) && (!b || ok_dt(in_dtypes[1])) && (!c || ok_dt(in_dtypes[2])), "add_layernorm: dtype");
-  add_layernorm_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      a, b, c, in_dtypes[0], b ? in_dtypes[1] : 0, c ? in_dtypes[2] : 0, b ? b_index : nullptr, gamma, beta, eps, (float*)y32, (__half*)y16,
-      relu, rows, dim);
+  const int nv = dim / 128;
+  const int db = b ? in_dtypes[1] : 0, dc = c ? in_dtypes[2] : 0;
+  const int64_t* bi = b ? b_index : nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+#define DPVO_LN_LAUNCH(NV, RPW)                                                                                              \
+  add_layernorm_kernel<NV, RPW><<<row_grid((rows + RPW - 1) / RPW), ROW_WARPS * 32, 0, st>>>(                              \
+      a, b, c, in_dtypes[0], db, dc, bi, gamma, beta, eps, (float*)y32, (__half*)y16, relu, rows, dim)
+  switch (nv) {
+    case 1: DPVO_LN_LAUNCH(1, 4); break;
+    case 2: DPVO_LN_LAUNCH(2, 2); break;
+    case 3: DPVO_LN_LAUNCH(3, 2); break;
+    case 4: DPVO_LN_LAUNCH(4, 2); break;
+    case 5: DPVO_LN_LAUNCH(5, 1); break;
+    case 6: DPVO_LN_LAUNCH(6, 1); break;
+    case 7: DPVO_LN_LAUNCH(7, 1); break;
+    default: DPVO_LN_LAUNCH(8, 1); break;
+  }
+#undef DPVO_LN_LAUNCH
   DPVO_LAUNCH_CHECK("add_layernorm_kernel");
   return DPVO_OK;
 }
