@@ -10,6 +10,7 @@
 // phases run inside one persistent kernel separated by a software grid barrier; there are no
 // floating-point or order-dependent atomics, so the result is bit-reproducible.
 #include "common.cuh"
+#include <cstring>
 
 namespace dpvo {
 
@@ -85,8 +86,12 @@ __device__ __forceinline__ int block_excl_scan(int v, int* smem_warp /*[G_WARPS+
 // One persistent kernel: ranges -> [count, scatter] per radix pass -> boundary flags -> group ids.
 // Two grid barriers per pass (every block derives its own scatter offsets from the tile-major
 // histogram instead of waiting for a scan block), one after the ranges, one before the final phase.
+// blockIdx.y selects one of (up to) two independent problems handled by the same launch: an update needs the edges
+// grouped by patch and by (source, target) frame, and the kernel is bound by the latency of its grid barriers,
+// not by work, so the second grouping rides along for free.  Barriers are per problem (own header, gridDim.x CTAs).
 __global__ void __launch_bounds__(G_THREADS)
-group_edges_kernel(const GroupArgs a) {
+group_edges_kernel(const GroupArgs a0, const GroupArgs a1) {
+  const GroupArgs& a = blockIdx.y ? a1 : a0;
   __shared__ unsigned warp_hist[G_WARPS][G_BINS];
   __shared__ int scan_tmp[G_WARPS + 1];
   __shared__ unsigned long long red[6];
@@ -318,44 +323,71 @@ static int64_t group_ws_bytes(int64_t E) {
   return align256(sizeof(GroupHeader)) + 2 * align256(E * 4) + align256(ntiles * (int64_t)G_BINS * 4) + align256((ntiles + 1) * 4);
 }
 
-static int group_launch(const int64_t* ka, const int64_t* kb, const int64_t* sec, int64_t E,
-                        int32_t* order, int32_t* group_of, int32_t* group_start,
-                        int64_t* gka, int64_t* gkb, int32_t* n_groups,
-                        void* ws, int64_t ws_bytes, cudaStream_t st) {
-  if (ws_bytes < group_ws_bytes(E)) {
-    set_error("group_edges: workspace %lld B < required %lld B", (long long)ws_bytes, (long long)group_ws_bytes(E));
+struct GroupProblem {
+  const int64_t* ka; const int64_t* kb; const int64_t* sec; int64_t E;
+  int32_t* order; int32_t* group_of; int32_t* group_start; int64_t* gka; int64_t* gkb; int32_t* n_groups;
+  void* ws; int64_t ws_bytes;
+};
+
+static int group_fill(const GroupProblem& p, GroupArgs& a, cudaStream_t st) {
+  const int64_t E = p.E;
+  if (p.ws_bytes < group_ws_bytes(E)) {
+    set_error("group_edges: workspace %lld B < required %lld B", (long long)p.ws_bytes, (long long)group_ws_bytes(E));
     return DPVO_ERR_WORKSPACE;
   }
   if (E >= (1ll << 31)) { set_error("group_edges: E too large"); return DPVO_ERR_UNSUPPORTED; }
-  GroupArgs a;
-  a.ka = ka; a.kb = kb; a.sec = sec; a.E = E; a.ntiles = (int)((E + G_TILE - 1) / G_TILE);
-  a.order = order; a.group_of = group_of; a.group_start = group_start;
-  a.group_key_a = gka; a.group_key_b = gkb; a.n_groups = n_groups;
-  char* p = (char*)ws;
-  a.hdr = (GroupHeader*)p; p += align256(sizeof(GroupHeader));
-  a.buf0 = (int32_t*)p; p += align256(E * 4);
-  a.buf1 = (int32_t*)p; p += align256(E * 4);
-  a.hist = (unsigned*)p; p += align256((int64_t)a.ntiles * G_BINS * 4);
-  a.tile_sums = (int32_t*)p;
+  a.ka = p.ka; a.kb = p.kb; a.sec = p.sec; a.E = E; a.ntiles = (int)((E + G_TILE - 1) / G_TILE);
+  a.order = p.order; a.group_of = p.group_of; a.group_start = p.group_start;
+  a.group_key_a = p.gka; a.group_key_b = p.gkb; a.n_groups = p.n_groups;
+  char* q = (char*)p.ws;
+  a.hdr = (GroupHeader*)q; q += align256(sizeof(GroupHeader));
+  a.buf0 = (int32_t*)q; q += align256(E * 4);
+  a.buf1 = (int32_t*)q; q += align256(E * 4);
+  a.hist = (unsigned*)q; q += align256((int64_t)a.ntiles * G_BINS * 4);
+  a.tile_sums = (int32_t*)q;
   int rc = check_cuda(cudaMemsetAsync(a.hdr, 0, sizeof(GroupHeader), st), "group_edges: memset");
   if (rc) return rc;
   if (E == 0) {
-    rc = check_cuda(cudaMemsetAsync(n_groups, 0, 4, st), "group_edges: memset");
+    rc = check_cuda(cudaMemsetAsync(p.n_groups, 0, 4, st), "group_edges: memset");
     if (rc) return rc;
-    return check_cuda(cudaMemsetAsync(group_start, 0, 4, st), "group_edges: memset");
+    return check_cuda(cudaMemsetAsync(p.group_start, 0, 4, st), "group_edges: memset");
   }
+  return DPVO_OK;
+}
+
+// one cooperative launch for one or two problems (second may be NULL)
+static int group_launch_n(const GroupProblem* p0, const GroupProblem* p1, cudaStream_t st) {
+  GroupArgs a0, a1;
+  memset(&a0, 0, sizeof(a0)); memset(&a1, 0, sizeof(a1));
+  int rc = group_fill(*p0, a0, st);
+  if (rc) return rc;
+  if (p1) { rc = group_fill(*p1, a1, st); if (rc) return rc; }
+  const bool two = p1 && p1->E > 0;
+  if (p0->E == 0 && !two) return DPVO_OK;
+  if (p0->E == 0) { a0 = a1; }                       // only the second problem has work: run it alone
+  const bool both = two && p0->E > 0;
   static int max_blocks = 0;
   if (max_blocks == 0) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, group_edges_kernel, G_THREADS, 0);
     max_blocks = std::max(1, per_sm) * sm_count();
   }
-  const int grid = std::min(a.ntiles, max_blocks);
-  void* kargs[] = {(void*)&a};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)group_edges_kernel, dim3(grid), dim3(G_THREADS), kargs, 0, st);
+  // both y-slices use the same x extent; the tile loops stride by gridDim.x, so any extent >= 1 is correct
+  const int want = both ? std::max(a0.ntiles, a1.ntiles) : a0.ntiles;
+  const int grid = std::max(1, std::min(want, max_blocks / (both ? 2 : 1)));
+  void* kargs[] = {(void*)&a0, (void*)&a1};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)group_edges_kernel, dim3(grid, both ? 2 : 1), dim3(G_THREADS), kargs, 0, st);
   if (e != cudaSuccess) return check_cuda(e, "group_edges_kernel");
   DPVO_LAUNCH_CHECK("group_edges_kernel");
   return DPVO_OK;
+}
+
+static int group_launch(const int64_t* ka, const int64_t* kb, const int64_t* sec, int64_t E,
+                        int32_t* order, int32_t* group_of, int32_t* group_start,
+                        int64_t* gka, int64_t* gkb, int32_t* n_groups,
+                        void* ws, int64_t ws_bytes, cudaStream_t st) {
+  GroupProblem p{ka, kb, sec, E, order, group_of, group_start, gka, gkb, n_groups, ws, ws_bytes};
+  return group_launch_n(&p, nullptr, st);
 }
 
 }  // namespace dpvo
@@ -373,6 +405,23 @@ extern "C" int dpvo_group_edges(const int64_t* key_a, const int64_t* key_b, cons
   DPVO_REQUIRE(E == 0 || key_a, "group_edges: null key");
   return group_launch(key_a, key_b, sec, E, order, group_of, group_start, group_key_a, group_key_b, n_groups,
                       workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dpvo_group_edges_pair(const int64_t* key_a0, const int64_t* key_b0, const int64_t* sec0,
+                                     int32_t* order0, int32_t* group_of0, int32_t* group_start0,
+                                     int64_t* group_key_a0, int64_t* group_key_b0, int32_t* n_groups0, void* workspace0,
+                                     const int64_t* key_a1, const int64_t* key_b1, const int64_t* sec1,
+                                     int32_t* order1, int32_t* group_of1, int32_t* group_start1,
+                                     int64_t* group_key_a1, int64_t* group_key_b1, int32_t* n_groups1, void* workspace1,
+                                     int64_t E, int64_t workspace_bytes_each, void* stream) {
+  DPVO_REQUIRE(E >= 0, "group_edges_pair: negative E");
+  DPVO_REQUIRE(order0 && group_of0 && group_start0 && group_key_a0 && n_groups0 && workspace0 && order1 && group_of1 && group_start1 &&
+               group_key_a1 && n_groups1 && workspace1, "group_edges_pair: null pointer");
+  DPVO_REQUIRE(E == 0 || (key_a0 && key_a1), "group_edges_pair: null key");
+  DPVO_REQUIRE(workspace0 != workspace1, "group_edges_pair: the two problems need separate workspaces");
+  GroupProblem p0{key_a0, key_b0, sec0, E, order0, group_of0, group_start0, group_key_a0, group_key_b0, n_groups0, workspace0, workspace_bytes_each};
+  GroupProblem p1{key_a1, key_b1, sec1, E, order1, group_of1, group_start1, group_key_a1, group_key_b1, n_groups1, workspace1, workspace_bytes_each};
+  return group_launch_n(&p0, &p1, (cudaStream_t)stream);
 }
 
 extern "C" int64_t dpvo_neighbors_workspace_bytes(int64_t E) {

@@ -316,6 +316,38 @@ std::vector<Tensor> group_edges(Tensor key_a, c10::optional<Tensor> key_b, c10::
   return {order, gof, gstart, ka, kbo, ng};
 }
 
+// both groupings of an update in one launch; returns the two 6-tuples of group_edges concatenated
+std::vector<Tensor> group_edges_pair(Tensor a0, c10::optional<Tensor> b0, c10::optional<Tensor> s0, Tensor a1, c10::optional<Tensor> b1,
+                                     c10::optional<Tensor> s1) {
+  need_cuda(a0, "key_a0");
+  c10::cuda::CUDAGuard guard(a0.device());
+  a0 = i64c(a0); a1 = i64c(a1);
+  const int64_t E = a0.numel();
+  TORCH_CHECK(a1.numel() == E, "group_edges_pair: both problems group the same edges");
+  Tensor kb[2], sc[2];
+  if (b0.has_value()) kb[0] = i64c(*b0);
+  if (s0.has_value()) sc[0] = i64c(*s0);
+  if (b1.has_value()) kb[1] = i64c(*b1);
+  if (s1.has_value()) sc[1] = i64c(*s1);
+  auto oi = a0.options().dtype(at::kInt);
+  const int64_t wsb = dpvo_group_workspace_bytes(E);
+  std::vector<Tensor> out;
+  Tensor ws[2];
+  for (int q = 0; q < 2; ++q) {
+    out.push_back(torch::empty({E}, oi)); out.push_back(torch::empty({E}, oi)); out.push_back(torch::empty({E + 1}, oi));
+    out.push_back(torch::empty({E}, a0.options())); out.push_back(torch::empty({E}, a0.options())); out.push_back(torch::empty({1}, oi));
+    ws[q] = byte_ws(wsb, a0);
+  }
+  auto P = [](const Tensor& t) -> const int64_t* { return t.defined() ? t.data_ptr<int64_t>() : nullptr; };
+  check(dpvo_group_edges_pair(a0.data_ptr<int64_t>(), P(kb[0]), P(sc[0]), out[0].data_ptr<int>(), out[1].data_ptr<int>(), out[2].data_ptr<int>(),
+                              out[3].data_ptr<int64_t>(), out[4].data_ptr<int64_t>(), out[5].data_ptr<int>(), ws[0].data_ptr(),
+                              a1.data_ptr<int64_t>(), P(kb[1]), P(sc[1]), out[6].data_ptr<int>(), out[7].data_ptr<int>(), out[8].data_ptr<int>(),
+                              out[9].data_ptr<int64_t>(), out[10].data_ptr<int64_t>(), out[11].data_ptr<int>(), ws[1].data_ptr(),
+                              E, wsb, stream()),
+        "dpvo_b200_ext.group_edges_pair");
+  return out;
+}
+
 // fastba.BA on groupings built once per update (order, group_start, key_a[, key_b], n of EdgeGroups)
 void ba_forward_grouped(Tensor poses, Tensor patches, Tensor intrinsics, Tensor target, Tensor weight, Tensor lmbda,
                         Tensor ii, Tensor jj, Tensor kk, int t0, int t1, int iterations,
@@ -539,6 +571,8 @@ PYBIND11_MODULE(lietorch_backends, m) {
 PYBIND11_MODULE(dpvo_b200_ext, m) {
   m.def("corr_pyramid2", &corr_pyramid2, "two-level fused correlation", py::arg("fmap1"), py::arg("fmap2_l0"), py::arg("fmap2_l1"),
         py::arg("coords"), py::arg("ii"), py::arg("jj"), py::arg("radius"), py::arg("div"), py::arg("pad_to") = 0, py::arg("out") = py::none());
+  m.def("group_edges_pair", &group_edges_pair, "two device edge groupings in one launch", py::arg("key_a0"), py::arg("key_b0"), py::arg("sec0"),
+        py::arg("key_a1"), py::arg("key_b1"), py::arg("sec1"));
   m.def("group_edges", &group_edges, "device edge grouping", py::arg("key_a"), py::arg("key_b") = py::none(),
         py::arg("sec") = py::none());
   m.def("ba_forward_grouped", &ba_forward_grouped, "fastba.BA on prebuilt edge groupings");

@@ -63,10 +63,17 @@ class SoftAgg(nn.Module):
 class EdgeGroups:
     """Device-resident CSR of an edge grouping (dpvo_group_edges); G bounds are host hints."""
 
-    def __init__(self, key_a, key_b=None, sec=None, max_groups=None):
-        ex = extensions()[3]
-        self.order, self.group_of, self.group_start, self.key_a, self.key_b, self.n = ex.group_edges(key_a, key_b, sec)
+    def __init__(self, key_a, key_b=None, sec=None, max_groups=None, _fields=None):
+        if _fields is None:
+            _fields = extensions()[3].group_edges(key_a, key_b, sec)
+        self.order, self.group_of, self.group_start, self.key_a, self.key_b, self.n = _fields
         self.max_groups = int(self.n.item()) if max_groups is None else int(max_groups)
+
+    @classmethod
+    def pair(cls, spec0, spec1, max_groups0=None, max_groups1=None):
+        """both groupings of an update -- spec = (key_a, key_b, sec) -- in one cooperative launch"""
+        f = extensions()[3].group_edges_pair(*spec0, *spec1)
+        return cls(None, max_groups=max_groups0, _fields=f[:6]), cls(None, max_groups=max_groups1, _fields=f[6:])
 
 
 class Update(nn.Module):

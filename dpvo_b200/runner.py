@@ -60,8 +60,7 @@ class UpdateRunner:
         corr = altcorr.corr_pyramid(s.gmap, (s.fmap1, s.fmap2), coords, self.kk_ring, self.jj_ring, 3, 4.0, 896, self.corr_buf)
         if ev is not None:
             ev["corr1"].record()
-        groups_kk = EdgeGroups(s.kk, None, s.jj, max_groups=self.max_patch_groups)
-        groups_ij = EdgeGroups(s.ii, s.jj, None, max_groups=self.max_pair_groups)
+        groups_kk, groups_ij = EdgeGroups.pair((s.kk, None, s.jj), (s.ii, s.jj, None), self.max_patch_groups, self.max_pair_groups)
         # context gather (dpvo.py:334) and target = centre + delta (dpvo.py:341) are folded into the
         # first LayerNorm pass and the heads kernel
         self.net, (target, weight, _) = self.update(self.net, s.imap, corr, None, s.ii, s.jj, s.kk, groups_kk, groups_ij,

@@ -161,6 +161,19 @@ int dpvo_group_edges(const int64_t* key_a, const int64_t* key_b, const int64_t* 
                      int32_t* order, int32_t* group_of, int32_t* group_start,
                      int64_t* group_key_a, int64_t* group_key_b, int32_t* n_groups,
                      void* workspace, int64_t workspace_bytes, void* stream);
+/*
+ * Two groupings of the same E edges in ONE cooperative launch (the kernel is bound by grid-barrier latency, so
+ * the second problem costs nothing): what one update needs -- by patch (kk, NULL, jj) for fastba.neighbors
+ * (ba.cpp:59-97) / agg_kk, and by frame pair (ii, jj, NULL) for agg_ij (net.py:87-88) and the BA pose blocks.
+ * Arguments as dpvo_group_edges, suffixed 0 / 1; each problem has its own workspace of workspace_bytes_each.
+ */
+int dpvo_group_edges_pair(const int64_t* key_a0, const int64_t* key_b0, const int64_t* sec0,
+                          int32_t* order0, int32_t* group_of0, int32_t* group_start0,
+                          int64_t* group_key_a0, int64_t* group_key_b0, int32_t* n_groups0, void* workspace0,
+                          const int64_t* key_a1, const int64_t* key_b1, const int64_t* sec1,
+                          int32_t* order1, int32_t* group_of1, int32_t* group_start1,
+                          int64_t* group_key_a1, int64_t* group_key_b1, int32_t* n_groups1, void* workspace1,
+                          int64_t E, int64_t workspace_bytes_each, void* stream);
 
 /*
  * neighbors from an existing grouping keyed by the edge's patch and ordered by target frame

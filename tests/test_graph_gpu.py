@@ -61,3 +61,22 @@ def test_neighbors_empty(ext):
     e = torch.zeros(0, dtype=torch.long, device=DEV)
     ix, jx = ext[1].neighbors(e, e)
     assert ix.numel() == 0 and jx.numel() == 0
+
+
+@pytest.mark.parametrize("E", [1, 777, 5000, 47712])
+def test_group_edges_pair_equals_two_single_launches(ext, E):
+    """both groupings of an update in one cooperative launch (grid.y = 2) are bit-identical to two launches"""
+    g = torch.Generator().manual_seed(E)
+    kk = torch.randint(0, 2300, (E,), generator=g).to(DEV)
+    ii = torch.randint(0, 36, (E,), generator=g).to(DEV)
+    jj = torch.randint(0, 36, (E,), generator=g).to(DEV)
+    a = ext[3].group_edges(kk, None, jj)
+    b = ext[3].group_edges(ii, jj, None)
+    p = ext[3].group_edges_pair(kk, None, jj, ii, jj, None)
+    na, nb = int(a[5]), int(b[5])
+    assert int(p[5]) == na and int(p[11]) == nb
+    for q, (one, n) in enumerate(((a, na), (b, nb))):
+        o = p[6 * q:6 * q + 6]
+        assert torch.equal(o[0], one[0]) and torch.equal(o[1], one[1])
+        assert torch.equal(o[2][:n + 1], one[2][:n + 1]) and torch.equal(o[3][:n], one[3][:n])
+    assert torch.equal(p[10][:nb], b[4][:nb])
