@@ -266,13 +266,17 @@ corr_fwd_mma(const CorrArgs a) {
   extern __shared__ __align__(16) unsigned char mma_smem_raw[];
   MmaWarpSmem& sm = reinterpret_cast<MmaWarpSmem*>(mma_smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int64_t nitems = a.list ? (int64_t)*a.list_count : (int64_t)a.B * a.M;
+  // list mode (edges the tcgen05 kernel could not box): an item is ONE patch pixel of a listed edge -- its own 8x8
+  // window on both levels and its 49 outputs -- so that the nine passes of a stretched edge spread over nine warps
+  // instead of serialising in one (a handful of such edges used to cost 30 us of single-warp latency)
+  const int64_t nitems = a.list ? (int64_t)*a.list_count * 9 : (int64_t)a.B * a.M;
   const int64_t wstride = (int64_t)gridDim.x * MMA_WARPS;
   const __half* f1 = reinterpret_cast<const __half*>(a.fmap1);
   __half* out = reinterpret_cast<__half*>(a.out);
 
   for (int64_t item = (int64_t)blockIdx.x * MMA_WARPS + (threadIdx.x >> 5); item < nitems; item += wstride) {
-    const int b = a.list ? 0 : (int)(item / a.M), m = a.list ? a.list[item] : (int)(item % a.M);
+    const int b = a.list ? 0 : (int)(item / a.M), m = a.list ? a.list[item / 9] : (int)(item % a.M);
+    const int psel = a.list ? (int)(item % 9) : -1;
     const int64_t ix = a.ii[m], jx = a.jj[m];
 
     // ---- patch features -> shared as [pixel][channel]
@@ -324,7 +328,7 @@ corr_fwd_mma(const CorrArgs a) {
       }
       const int bx_min = warp_min_i(ax), by_min = warp_min_i(ay);
       const int bx_max = warp_max_i(axm), by_max = warp_max_i(aym);
-      const bool uni = (bx_max - bx_min + D <= MMA_BOX) && (by_max - by_min + D <= MMA_BOX);
+      const bool uni = psel < 0 && (bx_max - bx_min + D <= MMA_BOX) && (by_max - by_min + D <= MMA_BOX);
       const int ubw = bx_max - bx_min + D;
       if (lane < 9) {
         sm.w[lev][lane] = make_float4((1.f - fx) * (1.f - fy), fx * (1.f - fy), (1.f - fx) * fy, fx * fy);
@@ -332,8 +336,8 @@ corr_fwd_mma(const CorrArgs a) {
         sm.pitch[lev][lane] = uni ? ubw : D;
       }
 
-      const int npass = uni ? 1 : 9;
-      for (int pass = 0; pass < npass; ++pass) {
+      const int pass0 = psel >= 0 ? psel : 0, npass = psel >= 0 ? psel + 1 : (uni ? 1 : 9);
+      for (int pass = pass0; pass < npass; ++pass) {
         const int bx0 = uni ? bx_min : __shfl_sync(0xffffffffu, ax, pass);
         const int by0 = uni ? by_min : __shfl_sync(0xffffffffu, ay, pass);
         const int bw = uni ? ubw : D;
@@ -398,7 +402,7 @@ corr_fwd_mma(const CorrArgs a) {
       const int xo0 = (tt0 * 37) >> 8, yo0 = tt0 - 7 * xo0;
       const int xo1 = (tt1 * 37) >> 8, yo1 = tt1 - 7 * xo1;
 #pragma unroll 1
-      for (int p = 0; p < 9; ++p) {
+      for (int p = (psel >= 0 ? psel : 0); p < (psel >= 0 ? psel + 1 : 9); ++p) {
         float v0[2] = {0.f, 0.f}, v1[2] = {0.f, 0.f};
 #pragma unroll
         for (int lev = 0; lev < 2; ++lev) {
@@ -420,7 +424,9 @@ corr_fwd_mma(const CorrArgs a) {
       __syncwarp();
       if constexpr (PAIR_OUT) {
         __half* orow = out + (int64_t)(b * a.M + m) * a.out_row;
-        if ((a.out_row & 7) == 0) {                            // 16-byte aligned rows (e.g. padded to 896)
+        if (psel >= 0) {                                       // one pixel: its 49 pairs, nine apart
+          for (int tt = lane; tt < O * O; tt += 32) reinterpret_cast<__half2*>(orow)[tt * 9 + psel] = stage[tt * 9 + psel];
+        } else if ((a.out_row & 7) == 0) {                            // 16-byte aligned rows (e.g. padded to 896)
           const uint4* s4 = reinterpret_cast<const uint4*>(stage);
           for (int i = lane; i < (NOUT * 4) / 16; i += 32) reinterpret_cast<uint4*>(orow)[i] = s4[i];
           if (lane == 0) reinterpret_cast<__half2*>(orow)[NOUT - 1] = stage[NOUT - 1];      // 441 = 4*110 + 1

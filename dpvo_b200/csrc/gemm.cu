@@ -49,6 +49,7 @@ struct GemmArgs {
   int64_t ldy16;
   int64_t rows; int N; int K; int epilogue;
   int prefetch;                // residual / gate tensor maps are valid: prefetch their tiles into L2
+  int exp_flags;               // perf experiments only (DPVO_B200_GEMM_EXP): 1 no residual load, 2 no gate load, 4 no Y store, 8 no Y16 store
   long long* dbg;              // optional per-role timestamps of CTA 0 (DPVO_B200_GEMM_TIMING), NULL = off
 };
 
@@ -175,9 +176,9 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  // The residual / gate tiles the epilogue of a tile will read are pulled into L2 while its MMAs run: the fp32
-  // state (73 MB) plus its fp16 copies do not fit L2, and at DRAM latency the epilogue's few loads in flight
-  // per lane bounded the fused layers at ~1.8 TB/s.
+  // Optional (DPVO_B200_GEMM_PREFETCH=1): pull the residual / gate tiles the epilogue of a tile will read into L2
+  // while its MMAs run.  Measured neutral to slightly negative once the epilogue prefetches a chunk ahead, so off
+  // by default.
   auto prefetch_epilogue_operands = [&](int m0, int n0) {
     if constexpr (EPI == DPVO_EPI_RESADD || EPI == DPVO_EPI_GATEDRES) {
       if (a.prefetch) {
@@ -344,9 +345,10 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int it = 0; it < 4; ++it) {
             if (ok[it] && c < nch) {
               const char* p = rp + it * rstep + c * (res32 ? 64 : 32);
-              if (res32) rv[it] = *reinterpret_cast<const float4*>(p);
+              if (a.exp_flags & 1) rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              else if (res32) rv[it] = *reinterpret_cast<const float4*>(p);
               else { const uint2 q = *reinterpret_cast<const uint2*>(p); rv[it] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), 0.f, 0.f); }
-              if constexpr (EPI == DPVO_EPI_GATEDRES) gv[it] = *reinterpret_cast<const uint2*>(gp + it * gstep + c * 32);
+              if constexpr (EPI == DPVO_EPI_GATEDRES) gv[it] = (a.exp_flags & 2) ? make_uint2(0u, 0u) : *reinterpret_cast<const uint2*>(gp + it * gstep + c * 32);
             }
           }
         }
@@ -413,9 +415,11 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(o4.x, o4.y);
           *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(o4.z, o4.w);
           if (ok[it]) {
-            if constexpr (OUT == GM_OUT_F16) *reinterpret_cast<uint2*>(yp + it * ystep + c * 32) = o;
-            else *reinterpret_cast<float4*>(yp + it * ystep + c * 64) = o4;
-            if constexpr (OUT == GM_OUT_F32_F16) *reinterpret_cast<uint2*>(y16p + it * y16step + c * 32) = o;
+            if (!(a.exp_flags & 4)) {
+              if constexpr (OUT == GM_OUT_F16) *reinterpret_cast<uint2*>(yp + it * ystep + c * 32) = o;
+              else *reinterpret_cast<float4*>(yp + it * ystep + c * 64) = o4;
+            }
+            if constexpr (OUT == GM_OUT_F32_F16) { if (!(a.exp_flags & 8)) *reinterpret_cast<uint2*>(y16p + it * y16step + c * 32) = o; }
           }
         }
       };
@@ -530,7 +534,7 @@ static int linear_launch(GemmArgs& a, cudaStream_t st) {
   int rc = make_tmap(&tmB, a.W, a.N, a.K, a.ldw, GM_N);
   if (rc) return rc;
   a.prefetch = 0;
-  if ((a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES) && !getenv("DPVO_B200_GEMM_NOPREFETCH")) {
+  if ((a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES) && getenv("DPVO_B200_GEMM_PREFETCH")) {
     bool ok = make_prefetch_tmap(&tmR, a.res, a.res_dtype, a.rows, a.N, a.ldres);
     if (ok && a.epilogue == DPVO_EPI_GATEDRES) ok = make_prefetch_tmap(&tmG, a.gate, DPVO_F16, a.rows, a.N, a.ldgate);
     a.prefetch = ok ? 1 : 0;
@@ -576,6 +580,10 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
   const bool timing = getenv("DPVO_B200_GEMM_TIMING") != nullptr;
   if (timing && !dbg) cudaMalloc(&dbg, 96 * sizeof(long long));
   a.dbg = timing ? dbg : nullptr;
+  {
+    const char* ex = getenv("DPVO_B200_GEMM_EXP");
+    a.exp_flags = ex ? atoi(ex) : 0;
+  }
   if (timing) cudaMemsetAsync(dbg, 0, 96 * sizeof(long long), (cudaStream_t)stream);
   const int rc = linear_launch(a, (cudaStream_t)stream);
   if (timing && rc == DPVO_OK) {

@@ -33,6 +33,16 @@ __device__ __forceinline__ void store4(void* base, int dtype, int64_t elem, floa
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+template <int DT> __device__ __forceinline__ float4 load4t(const void* base, int64_t elem) {
+  if constexpr (DT == DPVO_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
+  else {
+    const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + elem);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
 constexpr int ROW_WARPS = 8;
 constexpr int MAX_V4 = 8;     // up to 8 float4 per lane -> dim <= 1024
 
@@ -40,7 +50,9 @@ constexpr int MAX_V4 = 8;     // up to 8 float4 per lane -> dim <= 1024
 // NV = float4 per lane (dim = 128 NV, 3 for the update operator); a warp normalises RPW rows at a time so that
 // the loads of all of them are in flight before the first reduction (one row per warp and 70 registers left
 // the kernel at a third of the HBM rate: too few bytes in flight per SM).
-template <int NV, int RPW>
+// DA / DBC: element types of operand a and of operands b, c fixed at compile time (the three shapes the update
+// operator uses), or -1 = decided at run time from da / db / dc.
+template <int NV, int RPW, int DA, int DBC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, (NV * RPW <= 6) ? 3 : 2)
 add_layernorm_kernel(const void* a, const void* b, const void* c, int da, int db, int dc,
                      const int64_t* __restrict__ b_index,
@@ -60,9 +72,14 @@ add_layernorm_kernel(const void* a, const void* b, const void* c, int da, int db
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
         if (on) {
           const int64_t e = r * dim + (i * 32 + lane) * 4;
-          t = load4(a, da, e);
-          if (b) t = add4(t, load4(b, db, rb * dim + (i * 32 + lane) * 4));
-          if (c) t = add4(t, load4(c, dc, e));
+          if constexpr (DA >= 0) t = load4t<DA>(a, e); else t = load4(a, da, e);
+          if constexpr (DBC >= 0) {
+            if (b) t = add4(t, load4t<DBC>(b, rb * dim + (i * 32 + lane) * 4));
+            if (c) t = add4(t, load4t<DBC>(c, e));
+          } else {
+            if (b) t = add4(t, load4(b, db, rb * dim + (i * 32 + lane) * 4));
+            if (c) t = add4(t, load4(c, dc, e));
+          }
         }
         v[k][i] = t;
       }
@@ -200,34 +217,57 @@ softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ g
 }
 
 // ---- heads: out[r] = (Wd relu(net[r]) + bd, sigmoid(Ww relu(net[r]) + bw)) ---------------------
+// NV = float4 per lane (dim = 128 NV).  The four weight rows live in registers for the whole kernel and a warp
+// takes two rows of net at a time (loads of both in flight before the first reduction).
+template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 heads_kernel(const float* __restrict__ net, const float* __restrict__ W4, const float* __restrict__ b4,
              const float* __restrict__ coords, int PP, int centre,
              float* __restrict__ delta, float* __restrict__ weight, int64_t rows, int dim) {
   const int lane = threadIdx.x & 31;
-  for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * ROW_WARPS) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int col = lane * 4; col < dim; col += 128) {
-      float4 x = load4(net, DPVO_F32, r * dim + col);
-      x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+  float4 w[4][NV];
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const float4 w = *reinterpret_cast<const float4*>(W4 + o * dim + col);
-        acc[o] += (x.x * w.x + x.y * w.y) + (x.z * w.z + x.w * w.w);
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) w[o][i] = *reinterpret_cast<const float4*>(W4 + o * dim + (i * 32 + lane) * 4);
+  const float bias0 = b4[0], bias1 = b4[1], bias2 = b4[2], bias3 = b4[3];
+  const int64_t wstride = (int64_t)gridDim.x * ROW_WARPS * 2;
+  for (int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5)) * 2; r0 < rows; r0 += wstride) {
+    float4 x[2][NV];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        x[k][i] = (r0 + k < rows) ? *reinterpret_cast<const float4*>(net + (r0 + k) * dim + (i * 32 + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[2][4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[k][o] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 v = make_float4(fmaxf(x[k][i].x, 0.f), fmaxf(x[k][i].y, 0.f), fmaxf(x[k][i].z, 0.f), fmaxf(x[k][i].w, 0.f));
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[k][o] += (v.x * w[o][i].x + v.y * w[o][i].y) + (v.z * w[o][i].z + v.w * w[o][i].w);
       }
     }
 #pragma unroll
-    for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
-    if (lane == 0) {
-      float d0 = acc[0] + b4[0], d1 = acc[1] + b4[1];
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[k][o] = warp_sum(acc[k][o]);
+    if (lane < 2 && r0 + lane < rows) {
+      const int64_t r = r0 + lane;
+      const float a0 = lane ? acc[1][0] : acc[0][0], a1 = lane ? acc[1][1] : acc[0][1];
+      const float a2 = lane ? acc[1][2] : acc[0][2], a3 = lane ? acc[1][3] : acc[0][3];
+      float d0 = a0 + bias0, d1 = a1 + bias1;
       if (coords) {      // target = reprojected patch centre + delta (dpvo.py:341)
         d0 += coords[r * 2 * PP + centre];
         d1 += coords[r * 2 * PP + PP + centre];
       }
       delta[r * 2 + 0] = d0;
       delta[r * 2 + 1] = d1;
-      weight[r * 2 + 0] = sigmoidf_(acc[2] + b4[2]);
-      weight[r * 2 + 1] = sigmoidf_(acc[3] + b4[3]);
+      weight[r * 2 + 0] = sigmoidf_(a2 + bias2);
+      weight[r * 2 + 1] = sigmoidf_(a3 + bias3);
     }
   }
 }
@@ -254,9 +294,18 @@ extern "C" int dpvo_add_layernorm(const void* a, const void* b, const void* c, c
   const int db = b ? in_dtypes[1] : 0, dc = c ? in_dtypes[2] : 0;
   const int64_t* bi = b ? b_index : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-#define DPVO_LN_LAUNCH(NV, RPW)                                                                                              \
-  add_layernorm_kernel<NV, RPW><<<row_grid((rows + RPW - 1) / RPW), ROW_WARPS * 32, 0, st>>>(                              \
+#define DPVO_LN_LAUNCH_T(NV, RPW, DA, DBC)                                                                                   \
+  add_layernorm_kernel<NV, RPW, DA, DBC><<<row_grid((rows + RPW - 1) / RPW), ROW_WARPS * 32, 0, st>>>(                     \
       a, b, c, in_dtypes[0], db, dc, bi, gamma, beta, eps, (float*)y32, (__half*)y16, relu, rows, dim)
+#define DPVO_LN_LAUNCH(NV, RPW) DPVO_LN_LAUNCH_T(NV, RPW, -1, -1)
+  // the update operator's shapes (dim 384): fp16 alone, fp32 alone, fp32 + fp16 (+ fp16)
+  const bool bc16 = (!b || db == DPVO_F16) && (!c || dc == DPVO_F16);
+  if (nv == 3 && bc16) {
+    if (in_dtypes[0] == DPVO_F16) DPVO_LN_LAUNCH_T(3, 2, DPVO_F16, DPVO_F16);
+    else DPVO_LN_LAUNCH_T(3, 2, DPVO_F32, DPVO_F16);
+    DPVO_LAUNCH_CHECK("add_layernorm_kernel");
+    return DPVO_OK;
+  }
   switch (nv) {
     case 1: DPVO_LN_LAUNCH(1, 4); break;
     case 2: DPVO_LN_LAUNCH(2, 2); break;
@@ -268,6 +317,7 @@ extern "C" int dpvo_add_layernorm(const void* a, const void* b, const void* c, c
     default: DPVO_LN_LAUNCH(8, 1); break;
   }
 #undef DPVO_LN_LAUNCH
+#undef DPVO_LN_LAUNCH_T
   DPVO_LAUNCH_CHECK("add_layernorm_kernel");
   return DPVO_OK;
 }
@@ -319,11 +369,18 @@ extern "C" int dpvo_softagg_reduce(const void* f16, const void* g16, int64_t ld,
 
 extern "C" int dpvo_update_heads(const void* net32, const float* W4, const float* b4, const float* coords, int P,
                                  float* delta, float* weight, int64_t rows, int dim, void* stream) {
-  DPVO_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0, "update_heads: bad sizes");
+  DPVO_REQUIRE(rows >= 0 && dim > 0 && dim % 128 == 0 && dim <= 512, "update_heads: dim must be a multiple of 128, <= 512");
   if (rows == 0) return DPVO_OK;
   DPVO_REQUIRE(net32 && W4 && b4 && delta && weight, "update_heads: null pointer");
-  heads_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>((const float*)net32, W4, b4, coords, P * P, (P / 2) * P + P / 2,
-                                                                         delta, weight, rows, dim);
+  const unsigned grid = row_grid((rows + 1) / 2);
+  const int PP = P * P, centre = (P / 2) * P + P / 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dim / 128) {
+    case 1: heads_kernel<1><<<grid, ROW_WARPS * 32, 0, st>>>((const float*)net32, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
+    case 2: heads_kernel<2><<<grid, ROW_WARPS * 32, 0, st>>>((const float*)net32, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
+    case 3: heads_kernel<3><<<grid, ROW_WARPS * 32, 0, st>>>((const float*)net32, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
+    default: heads_kernel<4><<<grid, ROW_WARPS * 32, 0, st>>>((const float*)net32, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
+  }
   DPVO_LAUNCH_CHECK("heads_kernel");
   return DPVO_OK;
 }
