@@ -241,9 +241,34 @@ def run_ours(args):
     windows.append((w0, time.time()))
     launches = ex.launch_count() - l0
     run.timers = None
-    ms = t_start.elapsed_time(t_end) / args.steps
+    ms_eager = t_start.elapsed_time(t_end) / args.steps
+    ms = ms_eager
     corr_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(ev["corr0"], ev["corr1"]))
     ba_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(ev["ba0"], ev["ba1"]))
+
+    # ---- the same step as a CUDA graph (how the runner is meant to be driven): timed the same way.  The eager
+    # pass above stays for the per-stage breakdown (events cannot be recorded inside a graph).
+    launch_mode = "eager launches"
+    if not args.no_graph:
+        try:
+            run.capture()
+            for _ in range(3):
+                run.reset(); run.step_graph()
+            barrier()
+            w0 = time.time()
+            t_start.record()
+            for i in range(args.steps):
+                run.reset()
+                run.step_graph()
+            t_end.record()
+            barrier()
+            windows.append((w0, time.time()))
+            ms = t_start.elapsed_time(t_end) / args.steps
+            launch_mode = "CUDA graph replay (%d kernel nodes per step)" % (launches // args.steps)
+            launches *= 2                                  # kernels of the eager pass + of the replays
+        except Exception as exc:                           # noqa: BLE001 -- report and keep the eager number
+            run.graph = None
+            launch_mode = "eager launches (graph capture failed: %s)" % str(exc).splitlines()[0][:120]
 
     # ---- end to end: new frame from pinned host memory every step, poses + depths back to host
     hf = run.make_host_frame()
@@ -291,7 +316,8 @@ def run_ours(args):
     out = {"metric": METRIC, "value": world * 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f16 operands, f32 accumulate/state (BA f32)", "data": "synthetic", "config": workload_config(args.config, E),
-           "breakdown_ms": {"corr": corr_ms, "ba": ba_ms, "update_op_and_rest": ms - corr_ms - ba_ms, "gemm_backend": args.gemm},
+           "breakdown_ms": {"corr": corr_ms, "ba": ba_ms, "update_op_and_rest": ms_eager - corr_ms - ba_ms, "gemm_backend": args.gemm,
+                            "eager_ms_per_step": ms_eager, "launch": launch_mode},
            "e2e": {"value": world * 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches), "clocks": clocks,
            "roofline": {"kernel": "corr_fwd_tc (2-level patch correlation, tcgen05 + TMA)", "bound": "hbm", "achieved": ach, "peak": hbm,
@@ -313,6 +339,7 @@ def main():
     ap.add_argument("--config", default="default", choices=["default", "fast"])
     ap.add_argument("--gemm", default="tcgen05", choices=["cublas", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 200 if args.impl == "ours" else 4

@@ -384,7 +384,7 @@ int dt16or32(const Tensor& t) {
 }
 
 std::vector<Tensor> add_layernorm(Tensor a, c10::optional<Tensor> b, c10::optional<Tensor> c, Tensor gamma, Tensor beta,
-                                  double eps, bool relu, bool want32, bool want16, c10::optional<Tensor> b_index) {
+                                  double eps, bool relu, bool want32, bool want16, c10::optional<Tensor> b_index, bool inplace32) {
   need_cuda(a, "a");
   c10::cuda::CUDAGuard guard(a.device());
   const int dim = a.size(-1);
@@ -398,7 +398,10 @@ std::vector<Tensor> add_layernorm(Tensor a, c10::optional<Tensor> b, c10::option
   if (c.has_value()) { cc = c->contiguous(); dts[2] = dt16or32(cc); TORCH_CHECK(cc.numel() == a.numel(), "add_layernorm: shape mismatch"); }
   gamma = f32c(gamma); beta = f32c(beta);
   Tensor y32, y16;
-  if (want32) y32 = torch::empty(a.sizes(), a.options().dtype(at::kFloat));
+  // inplace32: the fp32 result overwrites operand a (rows are read completely before they are written), so a
+  // recurrent state can live in one buffer -- which also makes the whole update capturable in a CUDA graph
+  if (inplace32) TORCH_CHECK(want32 && a.scalar_type() == at::kFloat, "add_layernorm: inplace32 needs an fp32 operand a and want32");
+  if (want32) y32 = inplace32 ? a : torch::empty(a.sizes(), a.options().dtype(at::kFloat));
   if (want16) y16 = torch::empty(a.sizes(), a.options().dtype(at::kHalf));
   check(dpvo_add_layernorm(a.data_ptr(), bb.defined() ? bb.data_ptr() : nullptr, cc.defined() ? cc.data_ptr() : nullptr, dts,
                            bidx.defined() ? bidx.data_ptr<int64_t>() : nullptr, gamma.data_ptr<float>(), beta.data_ptr<float>(), (float)eps, want32 ? y32.data_ptr() : nullptr,
@@ -578,7 +581,7 @@ PYBIND11_MODULE(dpvo_b200_ext, m) {
   m.def("ba_forward_grouped", &ba_forward_grouped, "fastba.BA on prebuilt edge groupings");
   m.def("reproject_clamped", &reproject_clamped, "pops.transform-compatible fused reprojection");
   m.def("add_layernorm", &add_layernorm, "fused add + LayerNorm (+ReLU)", py::arg("a"), py::arg("b"), py::arg("c"), py::arg("gamma"),
-        py::arg("beta"), py::arg("eps"), py::arg("relu"), py::arg("want32"), py::arg("want16"), py::arg("b_index") = py::none());
+        py::arg("beta"), py::arg("eps"), py::arg("relu"), py::arg("want32"), py::arg("want16"), py::arg("b_index") = py::none(), py::arg("inplace32") = false);
   m.def("gather_rows_masked", &gather_rows_masked, "masked row gather");
   m.def("residual_add_", &residual_add_, "in-place residual add with optional row indirection");
   m.def("gated_residual", &gated_residual, "x + sigmoid(g) * r");

@@ -91,6 +91,7 @@ class Update(nn.Module):
         self.d = nn.Sequential(nn.ReLU(inplace=False), nn.Linear(DIM, 2), GradientClip())
         self.w = nn.Sequential(nn.ReLU(inplace=False), nn.Linear(DIM, 2), GradientClip(), nn.Sigmoid())
         self.gemm = gemm
+        self.inplace_state = False     # True: forward() overwrites an fp32 `net` argument with the new state
         self._packed = None
 
     # ------------------------------------------------------------------ packed inference weights
@@ -161,7 +162,10 @@ class Update(nn.Module):
         h = L(L(corr, "corr0", RELU), "corr2")
         _, h = ex.add_layernorm(h, None, None, self.corr[3].weight, self.corr[3].bias, 1e-3, True, False, True)
         h = L(h, "corr5")
-        net32, n16 = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, True, self._inp_index)
+        # the fp32 state is updated in place when the caller hands one in (contiguous fp32): the recurrent `net` then
+        # lives in a single buffer across updates
+        inplace = net.dtype == torch.float32 and net.is_contiguous() and self.inplace_state
+        net32, n16 = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, True, self._inp_index, inplace)
         ix, jx = ex.neighbors_from_groups(groups_kk.order, groups_kk.group_of)
         for idx, a, b in ((ix, "c1a", "c1b"), (jx, "c2a", "c2b")):
             u = L(n16, a, RELU, gather=idx)                       # c(mask * net[idx]) first layer
@@ -172,7 +176,7 @@ class Update(nn.Module):
             n16 = ex.residual_add_(net32, L(y, "h_" + nm), grp.group_of, True)
         x32 = net32
         for i, ln in ((1, self.gru[0]), (3, self.gru[2])):
-            x32, x16 = ex.add_layernorm(x32, None, None, ln.weight, ln.bias, 1e-3, False, True, True)
+            x32, x16 = ex.add_layernorm(x32, None, None, ln.weight, ln.bias, 1e-3, False, True, True, None, True)
             gate = L(x16, "gr%d_g" % i, SIGM)
             r1 = L(x16, "gr%d_a" % i, RELU)
             L(r1, "gr%d_b" % i, GATED, res=x32, gate=gate, out_f32=True, out=x32)

@@ -24,7 +24,9 @@ class UpdateRunner:
             update = Update(3, gemm=gemm)
         self.update = update.to(dev).eval()
         self.update.gemm = gemm
+        self.update.inplace_state = True               # `self.net` is one buffer, updated in place
         self.update.pack()
+        self.graph = None
         self.M = state.cfg["M"]
         self.mem = state.fmap1.shape[1]
         self.pmem = state.imap.shape[1] // self.M
@@ -73,6 +75,29 @@ class UpdateRunner:
             ev["ba1"].record()
         return target, weight
 
+    # ----------------------------------------------------------------------------- CUDA graph
+    def capture(self):
+        """Record one update() -- ~38 kernel launches, two memsets, no host decisions -- into a CUDA graph.
+        Every buffer the step touches is persistent (state, ring buffers, corr rows) or comes from the graph's
+        private pool, and the recurrent state is updated in place, so replaying the graph IS the next update."""
+        if self.timers is not None:
+            raise RuntimeError("capture(): event timers cannot be recorded inside a graph")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up off the capture: lazy inits, attribute calls
+            for _ in range(2):
+                self.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._graph_out = self.step()
+        return self.graph
+
+    def step_graph(self):
+        self.graph.replay()
+        return self._graph_out
+
     # ----------------------------------------------------------------- end to end (host buffers)
     def make_host_frame(self, seed=0):
         """pinned host copies of everything DPVO.__call__ writes for one new frame"""
@@ -106,7 +131,10 @@ class UpdateRunner:
         """ingest a frame from pinned host memory, update, read poses + patch depths back to host"""
         s = self.s
         h2d = self.ingest_frame(hf)
-        self.step()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.step()
         out_poses.copy_(s.poses[:s.n], non_blocking=True)
         out_depth.copy_(s.patches[:s.n * self.M, 2, 1, 1], non_blocking=True)
         return h2d, out_poses.numel() * 4 + out_depth.numel() * 4

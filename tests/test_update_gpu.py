@@ -111,3 +111,23 @@ def test_update_state_dict_keys_match_reference_names():
               "gru.1.gate.0.weight", "gru.3.res.2.bias", "corr.0.weight", "corr.3.weight", "corr.5.bias", "d.1.weight", "w.1.bias"):
         assert k in keys
     assert keys == set(OU.Update(3).state_dict().keys())
+
+
+def test_runner_graph_replay_equals_eager_steps(ext):
+    """UpdateRunner.capture(): replaying the CUDA graph is bit-identical to launching the kernels one by one,
+    including the recurrent state carried in place from one update to the next"""
+    from dpvo_b200.runner import UpdateRunner
+    outs = []
+    for use_graph in (False, True):
+        st = synthetic.make_state("fast", 14, device=DEV, seed=7)
+        run = UpdateRunner(st, gemm="tcgen05", seed=3)
+        if use_graph:
+            run.capture()                       # two warm-up steps + the captured one have advanced the state:
+            run.reset()                         # restore poses / patches and the recurrent state
+            run.net.zero_()
+        for _ in range(3):
+            tgt, wgt = run.step_graph() if use_graph else run.step()
+        torch.cuda.synchronize()
+        outs.append((st.poses.clone(), st.patches.clone(), run.net.clone(), tgt.clone(), wgt.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
