@@ -171,12 +171,18 @@ class Update(nn.Module):
             u = L(n16, a, RELU, gather=idx)                       # c(mask * net[idx]) first layer
             n16 = torch.empty_like(n16)
             L(u, b, RESADD, res=net32, out_f32=True, out=net32, out16=n16)   # net += second layer
-        for grp, nm in ((groups_kk, "kk"), (groups_ij, "ij")):
-            y = ex.softagg_reduce(L(n16, "fg_" + nm), grp.order, grp.group_start, grp.n, grp.max_groups)
-            n16 = ex.residual_add_(net32, L(y, "h_" + nm), grp.group_of, True)
+        y = ex.softagg_reduce(L(n16, "fg_kk"), groups_kk.order, groups_kk.group_start, groups_kk.n, groups_kk.max_groups)
+        n16 = ex.residual_add_(net32, L(y, "h_kk"), groups_kk.group_of, True)
+        y = ex.softagg_reduce(L(n16, "fg_ij"), groups_ij.order, groups_ij.group_start, groups_ij.n, groups_ij.max_groups)
+        h_ij = L(y, "h_ij")
         x32 = net32
         for i, ln in ((1, self.gru[0]), (3, self.gru[2])):
-            x32, x16 = ex.add_layernorm(x32, None, None, ln.weight, ln.bias, 1e-3, False, True, True, None, True)
+            if i == 1:
+                # net += h_ij[group] and the first LayerNorm of the GRU in one pass: the un-normalised sum is not
+                # needed again (net.py:88-90), so the scattered residual is just a gathered operand of the norm
+                x32, x16 = ex.add_layernorm(x32, h_ij, None, ln.weight, ln.bias, 1e-3, False, True, True, groups_ij.group_of.long(), True)
+            else:
+                x32, x16 = ex.add_layernorm(x32, None, None, ln.weight, ln.bias, 1e-3, False, True, True, None, True)
             gate = L(x16, "gr%d_g" % i, SIGM)
             r1 = L(x16, "gr%d_a" % i, RELU)
             L(r1, "gr%d_b" % i, GATED, res=x32, gate=gate, out_f32=True, out=x32)
