@@ -410,6 +410,12 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           } else if constexpr (EPI == DPVO_EPI_SIGMOID) {
             o4.x = __fdividef(1.0f, 1.0f + __expf(-o4.x)); o4.y = __fdividef(1.0f, 1.0f + __expf(-o4.y));
             o4.z = __fdividef(1.0f, 1.0f + __expf(-o4.z)); o4.w = __fdividef(1.0f, 1.0f + __expf(-o4.w));
+          } else if constexpr (EPI == DPVO_EPI_SIGMOID_RELU) {
+            const bool sg = n0 + c * 16 < (a.N >> 1);          // uniform over the chunk (N/2 is a multiple of 16)
+            o4.x = sg ? __fdividef(1.0f, 1.0f + __expf(-o4.x)) : fmaxf(o4.x, 0.f);
+            o4.y = sg ? __fdividef(1.0f, 1.0f + __expf(-o4.y)) : fmaxf(o4.y, 0.f);
+            o4.z = sg ? __fdividef(1.0f, 1.0f + __expf(-o4.z)) : fmaxf(o4.z, 0.f);
+            o4.w = sg ? __fdividef(1.0f, 1.0f + __expf(-o4.w)) : fmaxf(o4.w, 0.f);
           }
           uint2 o;
           *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(o4.x, o4.y);
@@ -504,6 +510,7 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     case DPVO_EPI_RELU: return launch_epi<GATHER, WS, DPVO_EPI_RELU>(tmA, tmB, tmR, tmG, a, grid, st);
     case DPVO_EPI_SIGMOID: return launch_epi<GATHER, WS, DPVO_EPI_SIGMOID>(tmA, tmB, tmR, tmG, a, grid, st);
     case DPVO_EPI_RESADD: return launch_epi<GATHER, WS, DPVO_EPI_RESADD>(tmA, tmB, tmR, tmG, a, grid, st);
+    case DPVO_EPI_SIGMOID_RELU: return launch_epi<GATHER, WS, DPVO_EPI_SIGMOID_RELU>(tmA, tmB, tmR, tmG, a, grid, st);
     default: return launch_epi<GATHER, WS, DPVO_EPI_GATEDRES>(tmA, tmB, tmR, tmG, a, grid, st);
   }
 }
@@ -560,7 +567,8 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
                "linear_f16: X / W rows must be 16-byte aligned");
   DPVO_REQUIRE(y_dtype == DPVO_F16 || y_dtype == DPVO_F32, "linear_f16: y dtype");
   DPVO_REQUIRE((y_dtype == DPVO_F16 ? ldy % 8 == 0 : ldy % 4 == 0) && ((uintptr_t)Y & 15) == 0, "linear_f16: Y rows must be 16-byte aligned");
-  DPVO_REQUIRE(epilogue >= DPVO_EPI_NONE && epilogue <= DPVO_EPI_GATEDRES, "linear_f16: unknown epilogue %d", epilogue);
+  DPVO_REQUIRE(epilogue >= DPVO_EPI_NONE && epilogue <= DPVO_EPI_SIGMOID_RELU, "linear_f16: unknown epilogue %d", epilogue);
+  DPVO_REQUIRE(epilogue != DPVO_EPI_SIGMOID_RELU || N % 32 == 0, "linear_f16: the split epilogue needs N/2 to be a multiple of 16");
   if (epilogue == DPVO_EPI_RESADD || epilogue == DPVO_EPI_GATEDRES)
     DPVO_REQUIRE(res && (res_dtype == DPVO_F16 || res_dtype == DPVO_F32), "linear_f16: residual operand missing");
   if (epilogue == DPVO_EPI_GATEDRES)

@@ -114,6 +114,9 @@ class Update(nn.Module):
             P["h_" + nm] = lin(agg.h)
         for i, blk in ((1, self.gru[1]), (3, self.gru[3])):
             P["gr%d_g" % i], P["gr%d_a" % i], P["gr%d_b" % i] = lin(blk.gate[0]), lin(blk.res[0]), lin(blk.res[2])
+            # gate and first residual layer share their input: one GEMM with N = 768 (sigmoid | relu halves)
+            (wg, bg), (wa, ba) = P["gr%d_g" % i], P["gr%d_a" % i]
+            P["gr%d_ga" % i] = (torch.cat([wg, wa], 0).contiguous(), torch.cat([bg, ba], 0).contiguous())
         P["heads_w"] = torch.cat([self.d[1].weight, self.w[1].weight], 0).detach().float().contiguous()
         P["heads_b"] = torch.cat([self.d[1].bias, self.w[1].bias], 0).detach().float().contiguous()
         self._packed = P
@@ -153,7 +156,7 @@ class Update(nn.Module):
         operand load and the epilogue"""
         ex = extensions()[3]
         P = self._packed or self.pack()
-        NONE, RELU, SIGM, RESADD, GATED = 0, 1, 2, 3, 4
+        NONE, RELU, SIGM, RESADD, GATED, SIGM_RELU = 0, 1, 2, 3, 4, 5
 
         def L(x, name, epi=NONE, **kw):
             wgt, b = P[name]
@@ -183,9 +186,8 @@ class Update(nn.Module):
                 x32, x16 = ex.add_layernorm(x32, h_ij, None, ln.weight, ln.bias, 1e-3, False, True, True, groups_ij.group_of.long(), True)
             else:
                 x32, x16 = ex.add_layernorm(x32, None, None, ln.weight, ln.bias, 1e-3, False, True, True, None, True)
-            gate = L(x16, "gr%d_g" % i, SIGM)
-            r1 = L(x16, "gr%d_a" % i, RELU)
-            L(r1, "gr%d_b" % i, GATED, res=x32, gate=gate, out_f32=True, out=x32)
+            ga = L(x16, "gr%d_ga" % i, SIGM_RELU)                  # [1, E, 768] = [sigmoid gate | relu(res layer 1)]
+            L(ga[..., DIM:], "gr%d_b" % i, GATED, res=x32, gate=ga[..., :DIM], out_f32=True, out=x32)
         delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"], self._coords)
         return x32, (delta, weight, None)
 

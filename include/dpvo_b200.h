@@ -350,6 +350,8 @@ int dpvo_update_heads(const void* net32, const float* W4, const float* b4, const
  *   DPVO_EPI_SIGMOID   y = sigmoid(acc + bias)
  *   DPVO_EPI_RESADD    y = res + acc + bias                       (res: [rows, N], F16/F32, stride ldres)
  *   DPVO_EPI_GATEDRES  y = res + gate * (acc + bias)              (gate: [rows, N] fp16, stride ldgate)
+ *   DPVO_EPI_SIGMOID_RELU  columns [0, N/2): sigmoid(acc + bias), columns [N/2, N): relu(acc + bias) -- two layers that
+ *                      share their input stacked into one GEMM (gate and first residual layer of GatedResidual, blocks.py:17-29)
  * Y dtype y_dtype (F16 or F32), row stride ldy; Y16 (optional) receives an fp16 copy of the same
  * result (row stride ldy16) so a following layer can consume it without another pass.  Y may alias
  * res.  K % 64 == 0 (pad 882 -> 896 with zeros), N % 32 == 0.  Row tails are handled.
@@ -359,6 +361,7 @@ int dpvo_update_heads(const void* net32, const float* W4, const float* b4, const
 #define DPVO_EPI_SIGMOID  2
 #define DPVO_EPI_RESADD   3
 #define DPVO_EPI_GATEDRES 4
+#define DPVO_EPI_SIGMOID_RELU 5
 int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather, const void* W, int64_t ldw,
                     const float* bias, const void* res, int res_dtype, int64_t ldres,
                     const void* gate, int64_t ldgate, void* Y, int y_dtype, int64_t ldy,

@@ -62,6 +62,25 @@ def test_linear_gather_residual_gate(ext):
     assert (y4[0] - ref4).abs().max().item() < 1e-3
 
 
+def test_linear_stacked_gate_and_strided_operands(ext):
+    """the GatedResidual block as the update operator runs it: gate and first residual layer stacked in one GEMM
+    (sigmoid | relu halves), whose two halves then feed the gated layer as STRIDED operand views"""
+    g = torch.Generator(device=DEV).manual_seed(9)
+    rows, D = 5000, 384
+    x = (torch.randn(rows, D, generator=g, device=DEV) * 0.5).half()
+    wg, wa, wb = [(torch.randn(D, D, generator=g, device=DEV) / D ** 0.5).half() for _ in range(3)]
+    bg, ba, bb = [torch.randn(D, generator=g, device=DEV) for _ in range(3)]
+    res = torch.randn(1, rows, D, generator=g, device=DEV)
+    ga = ext[3].linear_f16(x, torch.cat([wg, wa], 0).contiguous(), torch.cat([bg, ba], 0), 5)
+    assert ga.shape == (1, rows, 2 * D)
+    ref_gate, ref_r1 = _ref(x, wg, bg, 2), _ref(x, wa, ba, 1)
+    assert (ga[0, :, :D].float() - ref_gate).abs().max().item() < 2e-3
+    assert (ga[0, :, D:].float() - ref_r1).abs().max().item() <= 2e-3 * ref_r1.abs().max().item()
+    out = ext[3].linear_f16(ga[..., D:], wb, bb, 4, res=res, gate=ga[..., :D], out_f32=True)
+    ref = _ref(ga[0, :, D:], wb, bb, 4, res=res[0], gate=ga[0, :, :D])
+    assert (out[0] - ref).abs().max().item() < 1e-3
+
+
 def test_linear_no_bias_and_bad_shapes(ext):
     x = torch.randn(64, 128, device=DEV).half()
     w = torch.randn(64, 128, device=DEV).half()
