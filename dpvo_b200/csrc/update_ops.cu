@@ -175,20 +175,34 @@ gated_residual_kernel(const float* x, const __half* g, const __half* res, float*
   }
 }
 
-// ---- SoftAgg: one CTA per group, one thread per 2 channels, single pass online softmax --------
-// The rows of a group are scattered (order[]), so each step is a dependent global load; four rows are
-// requested before the first is consumed (the 74-edge (i,j) groups ran at one memory latency per edge).
+// ---- SoftAgg: one CTA per group, one thread per 2 channels ------------------------------------------------
+// Two passes over the group's (scattered) rows: the per-channel maximum of the logits with packed half2 compares,
+// then exp / sum / weighted sum.  The single-pass online softmax this replaces was issue-bound (a rescale test and
+// two extra exponentials per row); the second pass re-reads rows that are still in L1/L2.  Four rows are requested
+// before the first is consumed in both passes.
 __global__ void __launch_bounds__(256)
 softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ gl, int64_t ld,
                       const int32_t* __restrict__ order,
                       const int32_t* __restrict__ group_start, const int32_t* __restrict__ n_groups,
                       __half* __restrict__ y, int dim) {
   constexpr int PF = 4;
+  constexpr float LOG2E = 1.4426950408889634f;
   const int G = *n_groups;
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int s = group_start[g], e = group_start[g + 1];
     for (int col = threadIdx.x * 2; col < dim; col += blockDim.x * 2) {
-      float m0 = -INFINITY, m1 = -INFINITY, z0 = 0.f, z1 = 0.f, a0 = 0.f, a1 = 0.f;
+      __half2 mx = __float2half2_rn(-INFINITY);
+      for (int k0 = s; k0 < e; k0 += PF) {
+        __half2 gq[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+          gq[u] = (k0 + u < e) ? *reinterpret_cast<const __half2*>(gl + (int64_t)order[k0 + u] * ld + col) : mx;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) mx = __hmax2(mx, gq[u]);
+      }
+      const float2 m = __half22float2(mx);
+      const float m0 = m.x * LOG2E, m1 = m.y * LOG2E;
+      float z0 = 0.f, z1 = 0.f, a0 = 0.f, a1 = 0.f;
       for (int k0 = s; k0 < e; k0 += PF) {
         __half2 gq[PF], fq[PF];
 #pragma unroll
@@ -203,9 +217,7 @@ softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ g
         for (int u = 0; u < PF; ++u) {
           if (k0 + u < e) {
             const float2 gv = __half22float2(gq[u]), fv = __half22float2(fq[u]);
-            if (gv.x > m0) { const float sc = __expf(m0 - gv.x); z0 *= sc; a0 *= sc; m0 = gv.x; }
-            if (gv.y > m1) { const float sc = __expf(m1 - gv.y); z1 *= sc; a1 *= sc; m1 = gv.y; }
-            const float w0 = __expf(gv.x - m0), w1 = __expf(gv.y - m1);
+            const float w0 = exp2f(gv.x * LOG2E - m0), w1 = exp2f(gv.y * LOG2E - m1);   // exp(g - max), <= 1
             z0 += w0; a0 += w0 * fv.x;
             z1 += w1; a1 += w1 * fv.y;
           }
