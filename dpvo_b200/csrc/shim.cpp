@@ -384,7 +384,8 @@ int dt16or32(const Tensor& t) {
 }
 
 std::vector<Tensor> add_layernorm(Tensor a, c10::optional<Tensor> b, c10::optional<Tensor> c, Tensor gamma, Tensor beta,
-                                  double eps, bool relu, bool want32, bool want16, c10::optional<Tensor> b_index, bool inplace32) {
+                                  double eps, bool relu, bool want32, bool want16, c10::optional<Tensor> b_index, bool inplace32,
+                                  c10::optional<Tensor> c_scale) {
   need_cuda(a, "a");
   c10::cuda::CUDAGuard guard(a.device());
   const int dim = a.size(-1);
@@ -397,6 +398,12 @@ std::vector<Tensor> add_layernorm(Tensor a, c10::optional<Tensor> b, c10::option
   if (b.has_value()) { bb = b->contiguous(); dts[1] = dt16or32(bb); TORCH_CHECK(bidx.defined() || bb.numel() == a.numel(), "add_layernorm: shape mismatch"); }
   if (c.has_value()) { cc = c->contiguous(); dts[2] = dt16or32(cc); TORCH_CHECK(cc.numel() == a.numel(), "add_layernorm: shape mismatch"); }
   gamma = f32c(gamma); beta = f32c(beta);
+  Tensor csc; int64_t ld_cs = 0;
+  if (c_scale.has_value()) {
+    csc = c_scale->reshape({-1, dim});
+    TORCH_CHECK(csc.scalar_type() == at::kHalf && csc.stride(1) == 1 && csc.size(0) == rows && cc.defined(), "add_layernorm: c_scale must be fp16 [rows, dim] next to operand c");
+    ld_cs = csc.stride(0);
+  }
   Tensor y32, y16;
   // inplace32: the fp32 result overwrites operand a (rows are read completely before they are written), so a
   // recurrent state can live in one buffer -- which also makes the whole update capturable in a CUDA graph
@@ -404,7 +411,8 @@ std::vector<Tensor> add_layernorm(Tensor a, c10::optional<Tensor> b, c10::option
   if (want32) y32 = inplace32 ? a : torch::empty(a.sizes(), a.options().dtype(at::kFloat));
   if (want16) y16 = torch::empty(a.sizes(), a.options().dtype(at::kHalf));
   check(dpvo_add_layernorm(a.data_ptr(), bb.defined() ? bb.data_ptr() : nullptr, cc.defined() ? cc.data_ptr() : nullptr, dts,
-                           bidx.defined() ? bidx.data_ptr<int64_t>() : nullptr, gamma.data_ptr<float>(), beta.data_ptr<float>(), (float)eps, want32 ? y32.data_ptr() : nullptr,
+                           bidx.defined() ? bidx.data_ptr<int64_t>() : nullptr, csc.defined() ? csc.data_ptr() : nullptr, ld_cs,
+                           gamma.data_ptr<float>(), beta.data_ptr<float>(), (float)eps, want32 ? y32.data_ptr() : nullptr,
                            want16 ? y16.data_ptr() : nullptr, relu ? 1 : 0, rows, dim, stream()),
         "dpvo_b200_ext.add_layernorm");
   return {y32, y16};
@@ -512,10 +520,13 @@ std::vector<Tensor> neighbors_from_groups(Tensor order, Tensor group_of) {
   return {ix, jx};
 }
 
-std::vector<Tensor> update_heads(Tensor net32, Tensor W4, Tensor b4, c10::optional<Tensor> coords) {
+std::vector<Tensor> update_heads(Tensor net32, Tensor W4, Tensor b4, c10::optional<Tensor> coords, c10::optional<Tensor> gate,
+                                 c10::optional<Tensor> res) {
   need_cuda(net32, "net");
   c10::cuda::CUDAGuard guard(net32.device());
   TORCH_CHECK(net32.scalar_type() == at::kFloat, "update_heads: net must be float32");
+  TORCH_CHECK(gate.has_value() == res.has_value(), "update_heads: gate and res come together");
+  TORCH_CHECK(!gate.has_value() || net32.is_contiguous(), "update_heads: the gated form updates net in place and needs it contiguous");
   net32 = net32.contiguous(); W4 = f32c(W4); b4 = f32c(b4);
   const int dim = net32.size(-1);
   const int64_t rows = net32.numel() / dim;
@@ -523,7 +534,15 @@ std::vector<Tensor> update_heads(Tensor net32, Tensor W4, Tensor b4, c10::option
   Tensor delta = torch::empty({1, rows, 2}, net32.options()), weight = torch::empty({1, rows, 2}, net32.options());
   Tensor cd; int P = 1;
   if (coords.has_value()) { cd = f32c(*coords); P = cd.size(-1); TORCH_CHECK(cd.numel() == rows * 2 * P * P, "update_heads: coords must be [rows,2,P,P]"); }
-  check(dpvo_update_heads(net32.data_ptr(), W4.data_ptr<float>(), b4.data_ptr<float>(), cd.defined() ? cd.data_ptr<float>() : nullptr, P,
+  Tensor g2, r2; int64_t ldg = 0, ldr = 0;
+  if (gate.has_value()) {
+    g2 = gate->reshape({-1, dim}); r2 = res->reshape({-1, dim});
+    TORCH_CHECK(g2.scalar_type() == at::kHalf && r2.scalar_type() == at::kHalf && g2.stride(1) == 1 && r2.stride(1) == 1 && g2.size(0) == rows && r2.size(0) == rows,
+                "update_heads: gate / res must be fp16 [rows, dim]");
+    ldg = g2.stride(0); ldr = r2.stride(0);
+  }
+  check(dpvo_update_heads(net32.data_ptr(), g2.defined() ? g2.data_ptr() : nullptr, ldg, r2.defined() ? r2.data_ptr() : nullptr, ldr,
+                          W4.data_ptr<float>(), b4.data_ptr<float>(), cd.defined() ? cd.data_ptr<float>() : nullptr, P,
                           delta.data_ptr<float>(),
                           weight.data_ptr<float>(), rows, dim, stream()),
         "dpvo_b200_ext.update_heads");
@@ -581,13 +600,13 @@ PYBIND11_MODULE(dpvo_b200_ext, m) {
   m.def("ba_forward_grouped", &ba_forward_grouped, "fastba.BA on prebuilt edge groupings");
   m.def("reproject_clamped", &reproject_clamped, "pops.transform-compatible fused reprojection");
   m.def("add_layernorm", &add_layernorm, "fused add + LayerNorm (+ReLU)", py::arg("a"), py::arg("b"), py::arg("c"), py::arg("gamma"),
-        py::arg("beta"), py::arg("eps"), py::arg("relu"), py::arg("want32"), py::arg("want16"), py::arg("b_index") = py::none(), py::arg("inplace32") = false);
+        py::arg("beta"), py::arg("eps"), py::arg("relu"), py::arg("want32"), py::arg("want16"), py::arg("b_index") = py::none(), py::arg("inplace32") = false, py::arg("c_scale") = py::none());
   m.def("gather_rows_masked", &gather_rows_masked, "masked row gather");
   m.def("residual_add_", &residual_add_, "in-place residual add with optional row indirection");
   m.def("gated_residual", &gated_residual, "x + sigmoid(g) * r");
   m.def("softagg_reduce", &softagg_reduce, "segment softmax-weighted sum");
   m.def("update_heads", &update_heads, "delta / weight heads (optionally emitting the BA target)", py::arg("net32"), py::arg("W4"),
-        py::arg("b4"), py::arg("coords") = py::none());
+        py::arg("b4"), py::arg("coords") = py::none(), py::arg("gate") = py::none(), py::arg("res") = py::none());
   m.def("linear_f16", &linear_f16, "tcgen05 dense layer", py::arg("x"), py::arg("w"), py::arg("bias") = py::none(),
         py::arg("epilogue") = 0, py::arg("res") = py::none(), py::arg("gate") = py::none(), py::arg("gather") = py::none(),
         py::arg("out_f32") = false, py::arg("out") = py::none(), py::arg("out16") = py::none());

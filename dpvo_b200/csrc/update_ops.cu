@@ -55,7 +55,7 @@ constexpr int MAX_V4 = 8;     // up to 8 float4 per lane -> dim <= 1024
 template <int NV, int RPW, int DA, int DBC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, (NV * RPW <= 6) ? 3 : 2)
 add_layernorm_kernel(const void* a, const void* b, const void* c, int da, int db, int dc,
-                     const int64_t* __restrict__ b_index,
+                     const int64_t* __restrict__ b_index, const __half* __restrict__ cs, int64_t ld_cs,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      float* y32, __half* y16, int relu, int64_t rows, int dim) {
   const int lane = threadIdx.x & 31;
@@ -73,13 +73,19 @@ add_layernorm_kernel(const void* a, const void* b, const void* c, int da, int db
         if (on) {
           const int64_t e = r * dim + (i * 32 + lane) * 4;
           if constexpr (DA >= 0) t = load4t<DA>(a, e); else t = load4(a, da, e);
+          float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (DBC >= 0) {
             if (b) t = add4(t, load4t<DBC>(b, rb * dim + (i * 32 + lane) * 4));
-            if (c) t = add4(t, load4t<DBC>(c, e));
+            if (c) cv = load4t<DBC>(c, e);
           } else {
             if (b) t = add4(t, load4(b, db, rb * dim + (i * 32 + lane) * 4));
-            if (c) t = add4(t, load4(c, dc, e));
+            if (c) cv = load4(c, dc, e);
           }
+          if (cs) {                                            // operand c enters scaled element-wise: a + cs * c
+            const float4 g = load4t<DPVO_F16>(cs, r * ld_cs + (i * 32 + lane) * 4);
+            cv = make_float4(cv.x * g.x, cv.y * g.y, cv.z * g.z, cv.w * g.w);
+          }
+          t = add4(t, cv);
         }
         v[k][i] = t;
       }
@@ -231,9 +237,12 @@ softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ g
 // ---- heads: out[r] = (Wd relu(net[r]) + bd, sigmoid(Ww relu(net[r]) + bw)) ---------------------
 // NV = float4 per lane (dim = 128 NV).  The four weight rows live in registers for the whole kernel and a warp
 // takes two rows of net at a time (loads of both in flight before the first reduction).
+// Optional gated input: the row is x + gate * res (GatedResidual, blocks.py:28-29, gate already a sigmoid) and is
+// written back over x -- the last GatedResidual of the GRU folded into the pass that reads its output anyway.
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
-heads_kernel(const float* __restrict__ net, const float* __restrict__ W4, const float* __restrict__ b4,
+heads_kernel(float* net, const __half* __restrict__ gate, int64_t ld_gate, const __half* __restrict__ res, int64_t ld_res,
+             const float* __restrict__ W4, const float* __restrict__ b4,
              const float* __restrict__ coords, int PP, int centre,
              float* __restrict__ delta, float* __restrict__ weight, int64_t rows, int dim) {
   const int lane = threadIdx.x & 31;
@@ -250,7 +259,20 @@ heads_kernel(const float* __restrict__ net, const float* __restrict__ W4, const 
     for (int k = 0; k < 2; ++k)
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        x[k][i] = (r0 + k < rows) ? *reinterpret_cast<const float4*>(net + (r0 + k) * dim + (i * 32 + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        const int64_t r = r0 + k;
+        const int col = (i * 32 + lane) * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) {
+          t = *reinterpret_cast<const float4*>(net + r * dim + col);
+          if (gate) {
+            const float4 g = load4t<DPVO_F16>(gate, r * ld_gate + col), q = load4t<DPVO_F16>(res, r * ld_res + col);
+            t = make_float4(t.x + g.x * q.x, t.y + g.y * q.y, t.z + g.z * q.z, t.w + g.w * q.w);
+            *reinterpret_cast<float4*>(net + r * dim + col) = t;
+          }
+        }
+        x[k][i] = t;
+      }
     float acc[2][4];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -294,7 +316,7 @@ static inline bool ok_dt(int d) { return d == DPVO_F16 || d == DPVO_F32; }
 using namespace dpvo;
 
 extern "C" int dpvo_add_layernorm(const void* a, const void* b, const void* c, const int* in_dtypes,
-                                  const int64_t* b_index,
+                                  const int64_t* b_index, const void* c_scale, int64_t ld_c_scale,
                                   const float* gamma, const float* beta, float eps,
                                   void* y32, void* y16, int relu, int64_t rows, int dim, void* stream) {
   DPVO_REQUIRE(rows >= 0 && dim > 0, "add_layernorm: bad sizes");
@@ -302,13 +324,15 @@ extern "C" int dpvo_add_layernorm(const void* a, const void* b, const void* c, c
   DPVO_REQUIRE(a && in_dtypes && gamma && beta && (y32 || y16), "add_layernorm: null pointer");
   DPVO_REQUIRE(dim % 128 == 0 && dim <= 128 * MAX_V4, "add_layernorm: dim must be a multiple of 128, <= %d", 128 * MAX_V4);
   DPVO_REQUIRE(ok_dt(in_dtypes[0]) && (!b || ok_dt(in_dtypes[1])) && (!c || ok_dt(in_dtypes[2])), "add_layernorm: dtype");
+  DPVO_REQUIRE(!c_scale || (c && ld_c_scale >= dim && ld_c_scale % 4 == 0 && ((uintptr_t)c_scale & 7) == 0),
+               "add_layernorm: c_scale needs operand c and rows aligned to 4 elements");
   const int nv = dim / 128;
   const int db = b ? in_dtypes[1] : 0, dc = c ? in_dtypes[2] : 0;
   const int64_t* bi = b ? b_index : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
 #define DPVO_LN_LAUNCH_T(NV, RPW, DA, DBC)                                                                                   \
   add_layernorm_kernel<NV, RPW, DA, DBC><<<row_grid((rows + RPW - 1) / RPW), ROW_WARPS * 32, 0, st>>>(                     \
-      a, b, c, in_dtypes[0], db, dc, bi, gamma, beta, eps, (float*)y32, (__half*)y16, relu, rows, dim)
+      a, b, c, in_dtypes[0], db, dc, bi, (const __half*)c_scale, ld_c_scale, gamma, beta, eps, (float*)y32, (__half*)y16, relu, rows, dim)
 #define DPVO_LN_LAUNCH(NV, RPW) DPVO_LN_LAUNCH_T(NV, RPW, -1, -1)
   // the update operator's shapes (dim 384): fp16 alone, fp32 alone, fp32 + fp16 (+ fp16)
   const bool bc16 = (!b || db == DPVO_F16) && (!c || dc == DPVO_F16);
@@ -379,19 +403,23 @@ extern "C" int dpvo_softagg_reduce(const void* f16, const void* g16, int64_t ld,
   return DPVO_OK;
 }
 
-extern "C" int dpvo_update_heads(const void* net32, const float* W4, const float* b4, const float* coords, int P,
+extern "C" int dpvo_update_heads(void* net32, const void* gate16, int64_t ld_gate, const void* res16, int64_t ld_res,
+                                 const float* W4, const float* b4, const float* coords, int P,
                                  float* delta, float* weight, int64_t rows, int dim, void* stream) {
   DPVO_REQUIRE(rows >= 0 && dim > 0 && dim % 128 == 0 && dim <= 512, "update_heads: dim must be a multiple of 128, <= 512");
   if (rows == 0) return DPVO_OK;
   DPVO_REQUIRE(net32 && W4 && b4 && delta && weight, "update_heads: null pointer");
+  DPVO_REQUIRE((gate16 == nullptr) == (res16 == nullptr), "update_heads: gate and res come together");
+  DPVO_REQUIRE(!gate16 || (ld_gate % 4 == 0 && ld_res % 4 == 0 && ((uintptr_t)gate16 & 7) == 0 && ((uintptr_t)res16 & 7) == 0),
+               "update_heads: gate / res rows must be aligned to 4 elements");
   const unsigned grid = row_grid((rows + 1) / 2);
   const int PP = P * P, centre = (P / 2) * P + P / 2;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dim / 128) {
-    case 1: heads_kernel<1><<<grid, ROW_WARPS * 32, 0, st>>>((const float*)net32, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
-    case 2: heads_kernel<2><<<grid, ROW_WARPS * 32, 0, st>>>((const float*)net32, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
-    case 3: heads_kernel<3><<<grid, ROW_WARPS * 32, 0, st>>>((const float*)net32, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
-    default: heads_kernel<4><<<grid, ROW_WARPS * 32, 0, st>>>((const float*)net32, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
+    case 1: heads_kernel<1><<<grid, ROW_WARPS * 32, 0, st>>>((float*)net32, (const __half*)gate16, ld_gate, (const __half*)res16, ld_res, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
+    case 2: heads_kernel<2><<<grid, ROW_WARPS * 32, 0, st>>>((float*)net32, (const __half*)gate16, ld_gate, (const __half*)res16, ld_res, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
+    case 3: heads_kernel<3><<<grid, ROW_WARPS * 32, 0, st>>>((float*)net32, (const __half*)gate16, ld_gate, (const __half*)res16, ld_res, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
+    default: heads_kernel<4><<<grid, ROW_WARPS * 32, 0, st>>>((float*)net32, (const __half*)gate16, ld_gate, (const __half*)res16, ld_res, W4, b4, coords, PP, centre, delta, weight, rows, dim); break;
   }
   DPVO_LAUNCH_CHECK("heads_kernel");
   return DPVO_OK;

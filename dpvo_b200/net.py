@@ -178,17 +178,18 @@ class Update(nn.Module):
         n16 = ex.residual_add_(net32, L(y, "h_kk"), groups_kk.group_of, True)
         y = ex.softagg_reduce(L(n16, "fg_ij"), groups_ij.order, groups_ij.group_start, groups_ij.n, groups_ij.max_groups)
         h_ij = L(y, "h_ij")
+        # GRU (net.py:43-52): LN, GatedResidual, LN, GatedResidual.  Each GatedResidual x + gate * res is applied by
+        # the pass that consumes it (the second LayerNorm; the heads), so its last dense layer is a plain GEMM and
+        # the fp32 state is read and written once less per block.
         x32 = net32
-        for i, ln in ((1, self.gru[0]), (3, self.gru[2])):
-            if i == 1:
-                # net += h_ij[group] and the first LayerNorm of the GRU in one pass: the un-normalised sum is not
-                # needed again (net.py:88-90), so the scattered residual is just a gathered operand of the norm
-                x32, x16 = ex.add_layernorm(x32, h_ij, None, ln.weight, ln.bias, 1e-3, False, True, True, groups_ij.group_of.long(), True)
-            else:
-                x32, x16 = ex.add_layernorm(x32, None, None, ln.weight, ln.bias, 1e-3, False, True, True, None, True)
-            ga = L(x16, "gr%d_ga" % i, SIGM_RELU)                  # [1, E, 768] = [sigmoid gate | relu(res layer 1)]
-            L(ga[..., DIM:], "gr%d_b" % i, GATED, res=x32, gate=ga[..., :DIM], out_f32=True, out=x32)
-        delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"], self._coords)
+        # net += h_ij[group] and the first LayerNorm in one pass: the un-normalised sum is not needed again (net.py:88-90)
+        x32, x16 = ex.add_layernorm(x32, h_ij, None, self.gru[0].weight, self.gru[0].bias, 1e-3, False, True, True, groups_ij.group_of.long(), True)
+        ga = L(x16, "gr1_ga", SIGM_RELU)                           # [1, E, 768] = [sigmoid gate | relu(res layer 1)]
+        r2 = L(ga[..., DIM:], "gr1_b")
+        x32, x16 = ex.add_layernorm(x32, None, r2, self.gru[2].weight, self.gru[2].bias, 1e-3, False, True, True, None, True, ga[..., :DIM])
+        ga = L(x16, "gr3_ga", SIGM_RELU)
+        r2 = L(ga[..., DIM:], "gr3_b")
+        delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"], self._coords, ga[..., :DIM], r2)    # x32 <- x32 + gate * res
         return x32, (delta, weight, None)
 
     def _forward_cublas(self, net, inp, corr, groups_kk, groups_ij):

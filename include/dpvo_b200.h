@@ -297,9 +297,12 @@ int dpvo_lie_jinv(int group, int dtype, const void* X, const void* a, void* b, i
  * statistics in fp32.  Result written as fp32 (y32) and/or fp16 (y16) in the same pass.
  * b_index (optional, int64 [rows]): operand b is read from row b_index[r] -- the context gather
  * `imap[:, kk % (M*pmem)]` of dpvo.py:334 folded into the pass.
+ * c_scale (optional, fp16 [rows, dim] with row stride ld_c_scale): operand c enters as c_scale * c, i.e. the
+ * GatedResidual x + gate * res (blocks.py:28-29) that precedes the second LayerNorm of the GRU is folded in.
+ * y32 may alias a (rows are read completely before they are written).
  */
 int dpvo_add_layernorm(const void* a, const void* b, const void* c, const int* in_dtypes,
-                       const int64_t* b_index,
+                       const int64_t* b_index, const void* c_scale, int64_t ld_c_scale,
                        const float* gamma, const float* beta, float eps,
                        void* y32, void* y16, int relu, int64_t rows, int dim, void* stream);
 
@@ -334,8 +337,11 @@ int dpvo_softagg_reduce(const void* f16, const void* g16, int64_t ld, const int3
  * W4 fp32 [4, dim] = rows (Wd[0], Wd[1], Ww[0], Ww[1]); b4 fp32 [4]; delta, weight fp32 [rows, 2].
  * coords (optional, fp32 [rows, 2, P, P]): when given, `delta` receives the BA target
  * coords[:, :, P/2, P/2] + delta directly (dpvo.py:341).
+ * gate16 / res16 (optional, fp16 [rows, dim], row strides ld_gate / ld_res): the heads read net32 + gate16 * res16
+ * and that sum is written back to net32 -- the last GatedResidual of the GRU folded into this pass.
  */
-int dpvo_update_heads(const void* net32, const float* W4, const float* b4, const float* coords, int P,
+int dpvo_update_heads(void* net32, const void* gate16, int64_t ld_gate, const void* res16, int64_t ld_res,
+                      const float* W4, const float* b4, const float* coords, int P,
                       float* delta, float* weight, int64_t rows, int dim, void* stream);
 
 /*

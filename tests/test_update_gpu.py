@@ -54,6 +54,31 @@ def test_gather_residual_gate_heads(ext):
     assert (w.cpu().double() - torch.sigmoid(o[..., 2:])).abs().max().item() < 1e-5
 
 
+def test_gated_residual_folded_into_layernorm_and_heads(ext):
+    """x + gate * res applied by its consumer: as a scaled operand of add_layernorm (in place, strided gate view)
+    and as the gated input of the heads (which also writes the sum back)"""
+    g = torch.Generator().manual_seed(77)
+    E, D = 1500, 384
+    x = torch.randn(1, E, D, generator=g)
+    ga = torch.rand(1, E, 2 * D, generator=g).half()          # [gate | other half], gate is a strided view
+    r2 = torch.randn(1, E, D, generator=g).half()
+    gamma, beta = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g) * 0.1
+    s = x.double() + ga[..., :D].double() * r2.double()
+    ref = F.layer_norm(s, (D,), gamma.double(), beta.double(), 1e-3)
+    xd, gad = x.clone().to(DEV), ga.to(DEV)
+    y32, y16 = ext[3].add_layernorm(xd, None, r2.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-3, False, True, True, None, True, gad[..., :D])
+    assert y32.data_ptr() == xd.data_ptr()
+    assert (y32.cpu().double() - ref).abs().max().item() < 1e-4
+    assert (y16.cpu().double() - ref).abs().max().item() < 4e-3
+    W4, b4 = torch.randn(4, D, generator=g) / 20, torch.randn(4, generator=g)
+    xd = x.clone().to(DEV)
+    d, w = ext[3].update_heads(xd, W4.to(DEV), b4.to(DEV), None, gad[..., :D], r2.to(DEV))
+    assert (xd.cpu().double() - s).abs().max().item() < 1e-5               # the sum was written back
+    o = F.relu(s) @ W4.double().t() + b4.double()
+    assert (d.cpu().double() - o[..., :2]).abs().max().item() < 1e-4
+    assert (w.cpu().double() - torch.sigmoid(o[..., 2:])).abs().max().item() < 1e-4
+
+
 def test_softagg_reduce_matches_scatter_softmax(ext):
     g = torch.Generator().manual_seed(63)
     E, G = 5000, 137
