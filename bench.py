@@ -289,15 +289,21 @@ def run_ours(args):
     hf = run.make_host_frame()
     out_p = torch.empty(st.n, 7, pin_memory=True)
     out_d = torch.empty(st.n * run.M, pin_memory=True)
+    # frame t+1 is uploaded (pinned host -> staging, copy stream) while update t runs, as a streaming front end
+    # would; the first upload of the timed region is exposed, and there are exactly `steps` uploads in it
+    run.upload(hf)
     for _ in range(3):
-        run.reset(); run.step_e2e(hf, out_p, out_d)
+        run.reset(); run.step_e2e_pipelined(hf, out_p, out_d)
+    torch.cuda.synchronize()
+    run.step_e2e_pipelined(None, out_p, out_d)                 # drain the last warm-up upload
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     e0.record()
-    for _ in range(args.steps):
+    h2d = run.upload(hf)
+    for i in range(args.steps):
         run.reset()
-        h2d, d2h = run.step_e2e(hf, out_p, out_d)
+        _, d2h = run.step_e2e_pipelined(hf if i + 1 < args.steps else None, out_p, out_d)
         torch.cuda.current_stream().synchronize()          # the host consumes the result of every frame
     e1.record()
     barrier()
@@ -333,7 +339,9 @@ def run_ours(args):
            "dtype": "f16 operands, f32 accumulate/state (BA f32)", "data": "synthetic", "config": workload_config(args.config, E),
            "breakdown_ms": {"corr": corr_ms, "ba": ba_ms, "update_op_and_rest": ms_eager - corr_ms - ba_ms, "gemm_backend": args.gemm,
                             "eager_ms_per_step": ms_eager, "launch": launch_mode},
-           "e2e": {"value": world * 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "e2e": {"value": world * 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "pipeline": "frame t+1: pinned host -> staging on a copy stream while update t runs; staging -> ring slots, update (CUDA graph), "
+                               "D2H of poses + depths and a stream synchronize per frame on the compute stream"},
            "gpu_launches": int(launches), "clocks": clocks,
            "roofline": {"kernel": "corr_fwd_tc (2-level patch correlation, tcgen05 + TMA)", "bound": "hbm", "achieved": ach, "peak": hbm,
                         "unit": "GB/s", "frac": ach / hbm, "traffic": corr_dram_traffic() if args.config == "default" else None,

@@ -127,6 +127,39 @@ class UpdateRunner:
         s.poses[s.n - 1].copy_(hf["pose"], non_blocking=True)
         return sum(v.numel() * v.element_size() for v in hf.values())
 
+    # A streaming front end has frame t+1 in pinned memory while update t runs: its H2D copy goes to a staging
+    # buffer on a copy stream (overlapping the update), and only the short device-to-device move into the ring
+    # slots sits on the compute stream.
+    def upload(self, hf):
+        """start the H2D copy of a frame into the staging buffers (copy stream); returns the bytes copied"""
+        if not hasattr(self, "_staging"):
+            self._staging = {k: torch.empty_like(v, device=self.s.poses.device) for k, v in hf.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._ev_uploaded, self._ev_consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_consumed.record()
+        self._copy_stream.wait_event(self._ev_consumed)          # the previous frame has left the staging buffers
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in hf.items():
+                self._staging[k].copy_(v, non_blocking=True)
+            self._ev_uploaded.record()
+        return sum(v.numel() * v.element_size() for v in hf.values())
+
+    def step_e2e_pipelined(self, hf_next, out_poses, out_depth):
+        """consume the uploaded frame, start uploading the next one (if any), update, read the results back"""
+        s = self.s
+        main = torch.cuda.current_stream()
+        main.wait_event(self._ev_uploaded)
+        self.ingest_frame(self._staging)                           # device-to-device, a few microseconds
+        self._ev_consumed.record()
+        h2d = self.upload(hf_next) if hf_next is not None else 0
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.step()
+        out_poses.copy_(s.poses[:s.n], non_blocking=True)
+        out_depth.copy_(s.patches[:s.n * self.M, 2, 1, 1], non_blocking=True)
+        return h2d, out_poses.numel() * 4 + out_depth.numel() * 4
+
     def step_e2e(self, hf, out_poses, out_depth):
         """ingest a frame from pinned host memory, update, read poses + patch depths back to host"""
         s = self.s
