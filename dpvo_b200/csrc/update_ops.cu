@@ -13,6 +13,8 @@
 //   gated_residual       x + sigmoid(g) * r                              blocks.py:28-29
 //   heads                delta = Wd relu(net), weight = sigmoid(Ww relu(net))   net.py:62-71, 92
 #include "common.cuh"
+#include <cstdlib>
+#include <algorithm>
 
 namespace dpvo {
 
@@ -133,6 +135,202 @@ add_layernorm_kernel(const void* a, const void* b, const void* c, int da, int db
       }
     }
   }
+}
+
+// ---- add + LayerNorm, operands staged through shared memory by bulk copies ----------------------------------
+// The register kernel above keeps one or two rows per warp in flight -- at 80 registers and three CTAs per SM that
+// is ~36 KB per SM, a third of what the HBM latency-bandwidth product asks for -- so the dim = 384 shapes of the
+// update operator take this path: rows are dense, a tile of LNB_ROWS rows of operand a (and c) is ONE contiguous
+// range, fetched by a single cp.async.bulk per operand into a 4-deep ring by one thread; bytes in flight no longer
+// cost registers.  Gathered operand b and the strided scale of c are read directly (L2-resident, small).
+constexpr int LNB_ROWS = 16;          // rows per tile (two per warp)
+constexpr int LNB_STAGES = 4;
+constexpr int LNB_DIM = 384;
+constexpr size_t LNB_SMEM_CAP = 200 * 1024;
+
+__device__ __forceinline__ uint32_t lnb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Block = ROW_WARPS consumer warps + one producer warp (its lane 0 issues the copies of the tile three iterations
+// ahead while the consumers normalise the current one).
+template <int DA, bool HAS_C>
+__global__ void __launch_bounds__(ROW_WARPS * 32 + 32)
+add_layernorm_bulk_kernel(const void* a, const void* b, const __half* c, int db, const int64_t* __restrict__ b_index,
+                          const __half* __restrict__ cs, int64_t ld_cs,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                          float* y32, __half* y16, int relu, int64_t rows) {
+  constexpr int ES = (DA == DPVO_F32) ? 4 : 2;
+  constexpr int A_BYTES = LNB_ROWS * LNB_DIM * ES, C_BYTES = HAS_C ? LNB_ROWS * LNB_DIM * 2 : 0;
+  extern __shared__ __align__(128) unsigned char lnb_smem[];
+  constexpr int R_BYTES = LNB_ROWS * LNB_DIM * 2;                 // one fp16 tile (gathered b, scale of c)
+  unsigned char* sA = lnb_smem;                                   // [LNB_STAGES][A_BYTES]
+  unsigned char* sC = sA + LNB_STAGES * A_BYTES;                  // [LNB_STAGES][C_BYTES]
+  unsigned char* sB = sC + LNB_STAGES * C_BYTES;                  // [LNB_STAGES][R_BYTES] when b is given (fp16)
+  unsigned char* sS = sB + (b ? LNB_STAGES * R_BYTES : 0);        // [LNB_STAGES][R_BYTES] when cs is given
+  uint64_t* full = reinterpret_cast<uint64_t*>(sS + (cs ? LNB_STAGES * R_BYTES : 0));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_tiles = (rows + LNB_ROWS - 1) / LNB_ROWS;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LNB_STAGES; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(lnb_smem_u32(&full[i])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  // producer warp: lane 0 arms the barrier and copies the dense tiles of a and c with one bulk copy each; the rows
+  // of the gathered operand b and of the strided scale of c are 768-byte copies, one per lane
+  auto issue = [&](int64_t tile, int stage) {
+    const int64_t r0 = tile * LNB_ROWS;
+    const uint32_t nrow = (uint32_t)min((int64_t)LNB_ROWS, rows - r0);
+    const uint32_t bar = lnb_smem_u32(&full[stage]);
+    const uint32_t ba = nrow * LNB_DIM * ES, bc = HAS_C ? nrow * LNB_DIM * 2 : 0;
+    const uint32_t brow = LNB_DIM * 2, bb = b ? nrow * brow : 0, bs = cs ? nrow * brow : 0;
+    if (lane == 0) {
+      asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(bar), "r"(ba + bc + bb + bs) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(lnb_smem_u32(sA + stage * A_BYTES)),
+                   "l"(reinterpret_cast<const unsigned char*>(a) + r0 * LNB_DIM * ES), "r"(ba), "r"(bar)
+                   : "memory");
+      if constexpr (HAS_C)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(lnb_smem_u32(sC + stage * C_BYTES)),
+                     "l"(reinterpret_cast<const unsigned char*>(c) + r0 * LNB_DIM * 2), "r"(bc), "r"(bar)
+                     : "memory");
+    }
+    if ((uint32_t)lane < nrow) {
+      const uint32_t q = (uint32_t)lane;
+      if (b) {
+        const int64_t src = b_index ? b_index[r0 + q] : r0 + q;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(lnb_smem_u32(sB + stage * R_BYTES + q * brow)),
+                     "l"(reinterpret_cast<const unsigned char*>(b) + src * brow), "r"(brow), "r"(bar)
+                     : "memory");
+      }
+      if (cs)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(lnb_smem_u32(sS + stage * R_BYTES + q * brow)),
+                     "l"(reinterpret_cast<const unsigned char*>(cs) + (r0 + q) * ld_cs * 2), "r"(brow), "r"(bar)
+                     : "memory");
+    }
+  };
+  // gamma / beta of this lane's columns stay in registers
+  float4 gm[3], bt[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    gm[i] = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+    bt[i] = *reinterpret_cast<const float4*>(beta + (i * 32 + lane) * 4);
+  }
+  const bool producer = warp == ROW_WARPS;
+  if (producer)
+    for (int k = 0; k < LNB_STAGES - 1; ++k) {
+      const int64_t t = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+      if (t < n_tiles) issue(t, k);
+    }
+  int64_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int stage = (int)(it % LNB_STAGES);
+    if (producer) {                                               // into the stage freed by the previous iteration
+      const int64_t t = tile + (int64_t)(LNB_STAGES - 1) * gridDim.x;
+      if (t < n_tiles) issue(t, (int)((it + LNB_STAGES - 1) % LNB_STAGES));
+      __syncthreads();
+      continue;
+    }
+    {
+      const uint32_t bar = lnb_smem_u32(&full[stage]), parity = (uint32_t)((it / LNB_STAGES) & 1);
+      asm volatile(
+          "{\n.reg .pred p;\nLNB_WAIT_%=:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra LNB_DONE_%=;\nbra LNB_WAIT_%=;\nLNB_DONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+    }
+    const unsigned char* ta = sA + stage * A_BYTES;
+    const unsigned char* tc = sC + stage * C_BYTES;
+    const unsigned char* tb = sB + stage * R_BYTES;
+    const unsigned char* ts = sS + stage * R_BYTES;
+    float4 v[2][3];
+    int64_t rr[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int lr = warp * 2 + k;
+      const int64_t r = tile * LNB_ROWS + lr;
+      rr[k] = r;
+      const bool on = r < rows;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int col = (i * 32 + lane) * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
+          if constexpr (DA == DPVO_F32) t = *reinterpret_cast<const float4*>(ta + ((size_t)lr * LNB_DIM + col) * 4);
+          else t = load4t<DPVO_F16>(ta, (int64_t)lr * LNB_DIM + col);
+          if (b) t = add4(t, load4t<DPVO_F16>(tb, (int64_t)lr * LNB_DIM + col));
+          if constexpr (HAS_C) {
+            float4 cv = load4t<DPVO_F16>(tc, (int64_t)lr * LNB_DIM + col);
+            if (cs) {
+              const float4 g = load4t<DPVO_F16>(ts, (int64_t)lr * LNB_DIM + col);
+              cv = make_float4(cv.x * g.x, cv.y * g.y, cv.z * g.z, cv.w * g.w);
+            }
+            t = add4(t, cv);
+          }
+        }
+        v[k][i] = t;
+      }
+    }
+    float mean[2], rstd[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) sum += (v[k][i].x + v[k][i].y) + (v[k][i].z + v[k][i].w);
+      mean[k] = sum;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) mean[k] = warp_sum(mean[k]) / (float)LNB_DIM;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float dx = v[k][i].x - mean[k], dy = v[k][i].y - mean[k], dz = v[k][i].z - mean[k], dw = v[k][i].w - mean[k];
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+      rstd[k] = q;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) rstd[k] = rsqrtf(warp_sum(rstd[k]) / (float)LNB_DIM + eps);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (rr[k] < rows) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int col = (i * 32 + lane) * 4;
+          float4 o;
+          o.x = (v[k][i].x - mean[k]) * rstd[k] * gm[i].x + bt[i].x;
+          o.y = (v[k][i].y - mean[k]) * rstd[k] * gm[i].y + bt[i].y;
+          o.z = (v[k][i].z - mean[k]) * rstd[k] * gm[i].z + bt[i].z;
+          o.w = (v[k][i].w - mean[k]) * rstd[k] * gm[i].w + bt[i].w;
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (y32) store4(y32, DPVO_F32, rr[k] * LNB_DIM + col, o);
+          if (y16) store4(y16, DPVO_F16, rr[k] * LNB_DIM + col, o);
+        }
+      }
+    }
+    __syncthreads();                                              // every warp is done with this stage
+  }
+}
+
+template <int DA, bool HAS_C>
+static int launch_ln_bulk(const void* a, const void* b, const void* c, int db, const int64_t* bi, const void* cs, int64_t ld_cs,
+                          const float* gamma, const float* beta, float eps, void* y32, void* y16, int relu, int64_t rows, cudaStream_t st) {
+  constexpr int ES = (DA == DPVO_F32) ? 4 : 2;
+  const size_t smem = (size_t)LNB_STAGES * LNB_ROWS * LNB_DIM * (ES + (HAS_C ? 2 : 0) + (b ? 2 : 0) + (cs ? 2 : 0)) + LNB_STAGES * sizeof(uint64_t) + 128;
+  if (smem > LNB_SMEM_CAP) return DPVO_ERR_UNSUPPORTED;          // all four operands at once: the register kernel takes it
+  static bool attr = false;
+  if (!attr) {                                           // the largest layout (all four operands) of this instantiation
+    const size_t smem_max = std::min<size_t>(LNB_SMEM_CAP, (size_t)LNB_STAGES * LNB_ROWS * LNB_DIM * (ES + (HAS_C ? 2 : 0) + 4) + LNB_STAGES * sizeof(uint64_t) + 128);
+    cudaError_t e = cudaFuncSetAttribute(add_layernorm_bulk_kernel<DA, HAS_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if (e != cudaSuccess) return check_cuda(e, "add_layernorm: cudaFuncSetAttribute");
+    attr = true;
+  }
+  const int64_t n_tiles = (rows + LNB_ROWS - 1) / LNB_ROWS;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(200 * 1024) / smem));
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sm_count() * per_sm));
+  add_layernorm_bulk_kernel<DA, HAS_C><<<grid, ROW_WARPS * 32 + 32, smem, st>>>(a, b, (const __half*)c, db, bi, (const __half*)cs, ld_cs, gamma, beta, eps,
+                                                                           (float*)y32, (__half*)y16, relu, rows);
+  DPVO_LAUNCH_CHECK("add_layernorm_bulk_kernel");
+  return DPVO_OK;
 }
 
 // ---- gather / residual / scatter / gate -------------------------------------------------------
@@ -336,6 +534,19 @@ extern "C" int dpvo_add_layernorm(const void* a, const void* b, const void* c, c
 #define DPVO_LN_LAUNCH(NV, RPW) DPVO_LN_LAUNCH_T(NV, RPW, -1, -1)
   // the update operator's shapes (dim 384): fp16 alone, fp32 alone, fp32 + fp16 (+ fp16)
   const bool bc16 = (!b || db == DPVO_F16) && (!c || dc == DPVO_F16);
+  // dim 384, dense 16-byte aligned rows: operands a and c staged through shared memory by bulk copies
+  if (nv == 3 && bc16 && ROW_WARPS * 2 == LNB_ROWS && !getenv("DPVO_B200_LN_REGISTER") && ((uintptr_t)a & 15) == 0 &&
+      (!c || ((uintptr_t)c & 15) == 0) && (!b || ((uintptr_t)b & 15) == 0) &&
+      (!c_scale || (((uintptr_t)c_scale & 15) == 0 && (ld_c_scale * 2) % 16 == 0))) {
+    int rc;
+    if (in_dtypes[0] == DPVO_F16)
+      rc = c ? launch_ln_bulk<DPVO_F16, true>(a, b, c, db, bi, c_scale, ld_c_scale, gamma, beta, eps, y32, y16, relu, rows, st)
+             : launch_ln_bulk<DPVO_F16, false>(a, b, c, db, bi, c_scale, ld_c_scale, gamma, beta, eps, y32, y16, relu, rows, st);
+    else
+      rc = c ? launch_ln_bulk<DPVO_F32, true>(a, b, c, db, bi, c_scale, ld_c_scale, gamma, beta, eps, y32, y16, relu, rows, st)
+             : launch_ln_bulk<DPVO_F32, false>(a, b, c, db, bi, c_scale, ld_c_scale, gamma, beta, eps, y32, y16, relu, rows, st);
+    if (rc != DPVO_ERR_UNSUPPORTED) return rc;
+  }
   if (nv == 3 && bc16) {
     if (in_dtypes[0] == DPVO_F16) DPVO_LN_LAUNCH_T(3, 2, DPVO_F16, DPVO_F16);
     else DPVO_LN_LAUNCH_T(3, 2, DPVO_F32, DPVO_F16);
