@@ -387,6 +387,20 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           v[it] = stg[rr * 4 + (lc4 ^ ((rr >> 1) & 3))];
         }
         __syncwarp();                                        // staging tile free for the next chunk
+        if constexpr (EPI == DPVO_EPI_SIGMOID_RELU) {
+          // the column half decides the activation; uniform over the chunk (N/2 is a multiple of 16), so a real
+          // branch: evaluating both and selecting made this epilogue slower than the two layers it replaces
+          if (n0 + c * 16 < (a.N >> 1)) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+              v[it] = make_float4(__fdividef(1.0f, 1.0f + __expf(-(v[it].x + bv.x))), __fdividef(1.0f, 1.0f + __expf(-(v[it].y + bv.y))),
+                                  __fdividef(1.0f, 1.0f + __expf(-(v[it].z + bv.z))), __fdividef(1.0f, 1.0f + __expf(-(v[it].w + bv.w))));
+          } else {
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+              v[it] = make_float4(fmaxf(v[it].x + bv.x, 0.f), fmaxf(v[it].y + bv.y, 0.f), fmaxf(v[it].z + bv.z, 0.f), fmaxf(v[it].w + bv.w, 0.f));
+          }
+        }
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           float4 o4 = v[it];
@@ -411,11 +425,7 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             o4.x = __fdividef(1.0f, 1.0f + __expf(-o4.x)); o4.y = __fdividef(1.0f, 1.0f + __expf(-o4.y));
             o4.z = __fdividef(1.0f, 1.0f + __expf(-o4.z)); o4.w = __fdividef(1.0f, 1.0f + __expf(-o4.w));
           } else if constexpr (EPI == DPVO_EPI_SIGMOID_RELU) {
-            const bool sg = n0 + c * 16 < (a.N >> 1);          // uniform over the chunk (N/2 is a multiple of 16)
-            o4.x = sg ? __fdividef(1.0f, 1.0f + __expf(-o4.x)) : fmaxf(o4.x, 0.f);
-            o4.y = sg ? __fdividef(1.0f, 1.0f + __expf(-o4.y)) : fmaxf(o4.y, 0.f);
-            o4.z = sg ? __fdividef(1.0f, 1.0f + __expf(-o4.z)) : fmaxf(o4.z, 0.f);
-            o4.w = sg ? __fdividef(1.0f, 1.0f + __expf(-o4.w)) : fmaxf(o4.w, 0.f);
+            o4 = v[it];                                        // activated (with bias) before this loop, see below
           }
           uint2 o;
           *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(o4.x, o4.y);

@@ -433,8 +433,8 @@ softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ g
 }
 
 // ---- heads: out[r] = (Wd relu(net[r]) + bd, sigmoid(Ww relu(net[r]) + bw)) ---------------------
-// NV = float4 per lane (dim = 128 NV).  The four weight rows live in registers for the whole kernel and a warp
-// takes two rows of net at a time (loads of both in flight before the first reduction).
+// NV = float4 per lane (dim = 128 NV).  The four weight rows live in shared memory and a warp takes two rows of net
+// at a time (loads of both in flight before the first reduction).
 // Optional gated input: the row is x + gate * res (GatedResidual, blocks.py:28-29, gate already a sigmoid) and is
 // written back over x -- the last GatedResidual of the GRU folded into the pass that reads its output anyway.
 template <int NV>
@@ -444,33 +444,44 @@ heads_kernel(float* net, const __half* __restrict__ gate, int64_t ld_gate, const
              const float* __restrict__ coords, int PP, int centre,
              float* __restrict__ delta, float* __restrict__ weight, int64_t rows, int dim) {
   const int lane = threadIdx.x & 31;
-  float4 w[4][NV];
-#pragma unroll
-  for (int o = 0; o < 4; ++o)
-#pragma unroll
-    for (int i = 0; i < NV; ++i) w[o][i] = *reinterpret_cast<const float4*>(W4 + o * dim + (i * 32 + lane) * 4);
+  __shared__ float4 sw[4][NV * 32];                     // the four weight rows (6 KB at dim 384)
+  for (int i = threadIdx.x; i < 4 * NV * 32; i += blockDim.x) sw[i / (NV * 32)][i % (NV * 32)] = *reinterpret_cast<const float4*>(W4 + (size_t)i * 4);
+  __syncthreads();
   const float bias0 = b4[0], bias1 = b4[1], bias2 = b4[2], bias3 = b4[3];
   const int64_t wstride = (int64_t)gridDim.x * ROW_WARPS * 2;
   for (int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5)) * 2; r0 < rows; r0 += wstride) {
     float4 x[2][NV];
+    uint2 gq[2][NV], rq[2][NV];
+    // every load of both rows first (net may alias nothing here, but the compiler cannot know: a store between
+    // the loads would serialise them)
 #pragma unroll
     for (int k = 0; k < 2; ++k)
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-      {
+      for (int i = 0; i < NV; ++i) {
         const int64_t r = r0 + k;
         const int col = (i * 32 + lane) * 4;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        x[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gq[k][i] = make_uint2(0u, 0u); rq[k][i] = make_uint2(0u, 0u);
         if (r < rows) {
-          t = *reinterpret_cast<const float4*>(net + r * dim + col);
+          x[k][i] = *reinterpret_cast<const float4*>(net + r * dim + col);
           if (gate) {
-            const float4 g = load4t<DPVO_F16>(gate, r * ld_gate + col), q = load4t<DPVO_F16>(res, r * ld_res + col);
-            t = make_float4(t.x + g.x * q.x, t.y + g.y * q.y, t.z + g.z * q.z, t.w + g.w * q.w);
-            *reinterpret_cast<float4*>(net + r * dim + col) = t;
+            gq[k][i] = *reinterpret_cast<const uint2*>(gate + r * ld_gate + col);
+            rq[k][i] = *reinterpret_cast<const uint2*>(res + r * ld_res + col);
           }
         }
-        x[k][i] = t;
       }
+    if (gate) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int64_t r = r0 + k;
+          const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&gq[k][i].x)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&gq[k][i].y));
+          const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&rq[k][i].x)), q1 = __half22float2(*reinterpret_cast<const __half2*>(&rq[k][i].y));
+          x[k][i] = make_float4(x[k][i].x + g0.x * q0.x, x[k][i].y + g0.y * q0.y, x[k][i].z + g1.x * q1.x, x[k][i].w + g1.y * q1.y);
+          if (r < rows) *reinterpret_cast<float4*>(net + r * dim + (i * 32 + lane) * 4) = x[k][i];
+        }
+    }
     float acc[2][4];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -480,7 +491,10 @@ heads_kernel(float* net, const __half* __restrict__ gate, int64_t ld_gate, const
       for (int i = 0; i < NV; ++i) {
         const float4 v = make_float4(fmaxf(x[k][i].x, 0.f), fmaxf(x[k][i].y, 0.f), fmaxf(x[k][i].z, 0.f), fmaxf(x[k][i].w, 0.f));
 #pragma unroll
-        for (int o = 0; o < 4; ++o) acc[k][o] += (v.x * w[o][i].x + v.y * w[o][i].y) + (v.z * w[o][i].z + v.w * w[o][i].w);
+        for (int o = 0; o < 4; ++o) {
+          const float4 wv = sw[o][i * 32 + lane];
+          acc[k][o] += (v.x * wv.x + v.y * wv.y) + (v.z * wv.z + v.w * wv.w);
+        }
       }
     }
 #pragma unroll
