@@ -221,6 +221,21 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_u32(sB + kb * GM_B_BYTES), &tmB, kb * GM_K, n0, &bars->wfull);
         }
       }
+      // source rows of this thread's eight 16-byte chunks, fetched one tile ahead: the dependent index load would
+      // otherwise open every tile with a global-memory latency during which nothing is in flight
+      int64_t nsrc[8];
+      auto fetch_rows = [&](int64_t tile) {
+        const int64_t m0 = (tile / n_tiles_n) * GM_M;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = (pt + GM_PROD_THREADS * i) >> 3;
+          int64_t src = m0 + row;
+          if (tile >= n_tiles || src >= a.rows) src = -1;
+          else if (a.gather) src = a.gather[src];
+          nsrc[i] = src;
+        }
+      };
+      fetch_rows(blockIdx.x);
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t m0 = (tile / n_tiles_n) * GM_M;
         const int n0 = (int)(tile % n_tiles_n) * GM_N;
@@ -229,13 +244,13 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int c = pt + GM_PROD_THREADS * i, row = c >> 3, ch = c & 7;
-          int64_t src = m0 + row;
-          bool ok = src < a.rows;
-          if (ok && a.gather) { src = a.gather[src]; ok = src >= 0; }
+          const int64_t src = nsrc[i];
+          const bool ok = src >= 0;
           arow[i] = a.X + (ok ? src : 0) * a.ldx + ch * 8;
           abytes[i] = ok ? 16u : 0u;
           aoff[i] = row * 128 + ((ch ^ (row & 7)) << 4);
         }
+        fetch_rows(tile + gridDim.x);
         const __half* brow[12]; uint32_t boff[12], bbytes[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) {

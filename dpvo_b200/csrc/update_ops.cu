@@ -379,55 +379,80 @@ gated_residual_kernel(const float* x, const __half* g, const __half* res, float*
   }
 }
 
-// ---- SoftAgg: one CTA per group, one thread per 2 channels ------------------------------------------------
+// ---- SoftAgg: one CTA per group, SA_SPLIT threads per 2 channels -------------------------------------------
 // Two passes over the group's (scattered) rows: the per-channel maximum of the logits with packed half2 compares,
 // then exp / sum / weighted sum.  The single-pass online softmax this replaces was issue-bound (a rescale test and
-// two extra exponentials per row); the second pass re-reads rows that are still in L1/L2.  Four rows are requested
-// before the first is consumed in both passes.
-__global__ void __launch_bounds__(256)
+// two extra exponentials per row); the second pass re-reads rows that are still in L1/L2.  The rows of a group are
+// dealt round-robin to SA_SPLIT thread groups (a (source, target) group has ~100 rows and there are fewer such
+// groups than CTA slots), partial maxima / sums are combined through shared memory in a fixed order, and four
+// rows are requested before the first is consumed in both passes.
+constexpr int SA_SPLIT = 2;
+constexpr int SA_MAXPAIRS = 256;      // channel pairs per CTA pass (dim <= 512 per pass)
+
+__global__ void __launch_bounds__(SA_SPLIT * SA_MAXPAIRS)
 softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ gl, int64_t ld,
                       const int32_t* __restrict__ order,
                       const int32_t* __restrict__ group_start, const int32_t* __restrict__ n_groups,
                       __half* __restrict__ y, int dim) {
   constexpr int PF = 4;
   constexpr float LOG2E = 1.4426950408889634f;
+  __shared__ __half2 s_max[SA_SPLIT][SA_MAXPAIRS];
+  __shared__ float4 s_part[SA_SPLIT][SA_MAXPAIRS];
   const int G = *n_groups;
+  const int npairs = blockDim.x / SA_SPLIT;                 // channel pairs handled per pass
+  const int pr = threadIdx.x % npairs, sp = threadIdx.x / npairs;
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
     const int s = group_start[g], e = group_start[g + 1];
-    for (int col = threadIdx.x * 2; col < dim; col += blockDim.x * 2) {
+    for (int col0 = 0; col0 < dim; col0 += npairs * 2) {
+      const int col = col0 + pr * 2;
+      const bool on = col < dim;
       __half2 mx = __float2half2_rn(-INFINITY);
-      for (int k0 = s; k0 < e; k0 += PF) {
-        __half2 gq[PF];
+      if (on)
+        for (int k0 = s + sp * PF; k0 < e; k0 += PF * SA_SPLIT) {
+          __half2 gq[PF];
 #pragma unroll
-        for (int u = 0; u < PF; ++u)
-          gq[u] = (k0 + u < e) ? *reinterpret_cast<const __half2*>(gl + (int64_t)order[k0 + u] * ld + col) : mx;
+          for (int u = 0; u < PF; ++u)
+            gq[u] = (k0 + u < e) ? *reinterpret_cast<const __half2*>(gl + (int64_t)order[k0 + u] * ld + col) : mx;
 #pragma unroll
-        for (int u = 0; u < PF; ++u) mx = __hmax2(mx, gq[u]);
-      }
+          for (int u = 0; u < PF; ++u) mx = __hmax2(mx, gq[u]);
+        }
+      s_max[sp][pr] = mx;
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < SA_SPLIT; ++q) mx = __hmax2(mx, s_max[q][pr]);
       const float2 m = __half22float2(mx);
       const float m0 = m.x * LOG2E, m1 = m.y * LOG2E;
       float z0 = 0.f, z1 = 0.f, a0 = 0.f, a1 = 0.f;
-      for (int k0 = s; k0 < e; k0 += PF) {
-        __half2 gq[PF], fq[PF];
+      if (on)
+        for (int k0 = s + sp * PF; k0 < e; k0 += PF * SA_SPLIT) {
+          __half2 gq[PF], fq[PF];
 #pragma unroll
-        for (int u = 0; u < PF; ++u) {
-          if (k0 + u < e) {
-            const int64_t row = (int64_t)order[k0 + u] * ld + col;
-            gq[u] = *reinterpret_cast<const __half2*>(gl + row);
-            fq[u] = *reinterpret_cast<const __half2*>(f + row);
+          for (int u = 0; u < PF; ++u) {
+            if (k0 + u < e) {
+              const int64_t row = (int64_t)order[k0 + u] * ld + col;
+              gq[u] = *reinterpret_cast<const __half2*>(gl + row);
+              fq[u] = *reinterpret_cast<const __half2*>(f + row);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < PF; ++u) {
+            if (k0 + u < e) {
+              const float2 gv = __half22float2(gq[u]), fv = __half22float2(fq[u]);
+              const float w0 = exp2f(gv.x * LOG2E - m0), w1 = exp2f(gv.y * LOG2E - m1);   // exp(g - max), <= 1
+              z0 += w0; a0 += w0 * fv.x;
+              z1 += w1; a1 += w1 * fv.y;
+            }
           }
         }
+      s_part[sp][pr] = make_float4(z0, a0, z1, a1);
+      __syncthreads();
+      if (sp == 0 && on) {
+        float zz0 = 0.f, aa0 = 0.f, zz1 = 0.f, aa1 = 0.f;
 #pragma unroll
-        for (int u = 0; u < PF; ++u) {
-          if (k0 + u < e) {
-            const float2 gv = __half22float2(gq[u]), fv = __half22float2(fq[u]);
-            const float w0 = exp2f(gv.x * LOG2E - m0), w1 = exp2f(gv.y * LOG2E - m1);   // exp(g - max), <= 1
-            z0 += w0; a0 += w0 * fv.x;
-            z1 += w1; a1 += w1 * fv.y;
-          }
-        }
+        for (int q = 0; q < SA_SPLIT; ++q) { const float4 p = s_part[q][pr]; zz0 += p.x; aa0 += p.y; zz1 += p.z; aa1 += p.w; }
+        *reinterpret_cast<__half2*>(y + (int64_t)g * dim + col) = __floats2half2_rn(aa0 / zz0, aa1 / zz1);
       }
-      *reinterpret_cast<__half2*>(y + (int64_t)g * dim + col) = __floats2half2_rn(a0 / z0, a1 / z1);
+      __syncthreads();
     }
   }
 }
@@ -621,7 +646,8 @@ extern "C" int dpvo_softagg_reduce(const void* f16, const void* g16, int64_t ld,
   DPVO_REQUIRE(f16 && g16 && order && group_start && n_groups && y16, "softagg_reduce: null pointer");
   DPVO_REQUIRE(ld >= dim && ld % 2 == 0, "softagg_reduce: row stride must be even and >= dim");
   const unsigned grid = (unsigned)std::min<int64_t>(max_groups, (int64_t)sm_count() * 8);
-  const int threads = std::min(256, std::max(32, ((dim / 2 + 31) / 32) * 32));
+  const int pairs = std::min(SA_MAXPAIRS, std::max(32, ((dim / 2 + 31) / 32) * 32));
+  const int threads = pairs * SA_SPLIT;
   softagg_reduce_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)f16, (const __half*)g16, ld, order, group_start,
                                                                    n_groups, (__half*)y16, dim);
   DPVO_LAUNCH_CHECK("softagg_reduce_kernel");
