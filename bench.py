@@ -349,7 +349,7 @@ def run_ours(args):
                                         "(L2 reuse of the feature ring keeps it below the algorithmic bytes, so frac can exceed 1)",
                         "peak_source": which,
                         "algorithmic_bytes_per_launch": BYTES_PER_EDGE_FP16 * E, "kernel_ms": corr_ms}}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU leg is timed at N = 1 only
         val, threads, sample, _ = cpu_reference_measure(args.config, 2, 1, 20.0)
         out["cpu_baseline"] = {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample}
     print(json.dumps(out))
