@@ -48,6 +48,26 @@ def test_ba_forward_matches_oracle(ext, config, n_frames, iters):
     assert _rel(poses[0].cpu().double()[t0:t1] - st.poses.double()[t0:t1], rp[t0:t1] - st.poses.double()[t0:t1]) < 2e-3
 
 
+@pytest.mark.parametrize("t0", [2, 12])
+def test_ba_many_free_poses(ext, t0):
+    """wide optimisation windows (28 and 18 free poses of the 32 the on-chip solver holds): the Schur tiles no
+    longer fit one round of the CTA, the Cholesky runs 28 panels"""
+    st, target, weight = _problem("fast", 30, 23, sigma=0.5)
+    lm = torch.tensor([1e-4])
+    t1 = st.n
+    rp, rpatch = OB.fastba_forward(st.poses.double(), st.patches.double(), st.intrinsics.double(), target.double(),
+                                   weight.double(), lm.double(), st.ii, st.jj, st.kk, t0, t1, 2)
+    poses = st.poses.clone().to(DEV)[None]
+    patches = st.patches.clone().to(DEV)[None]
+    ext[1].forward(poses, patches, st.intrinsics.to(DEV)[None], target.to(DEV)[None], weight.to(DEV)[None], lm.to(DEV),
+                   st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV), st.cfg["M"], t0, t1, 2, False)
+    torch.cuda.synchronize()
+    assert _rel(poses[0].cpu().double()[:t1], rp[:t1]) < 1e-4
+    live = st.kk.unique()
+    assert _rel(patches[0].cpu().double()[live, 2], rpatch[live, 2]) < 1e-4
+    assert torch.equal(poses[0, :t0].cpu(), st.poses[:t0])
+
+
 def test_ba_is_deterministic(ext):
     st, target, weight = _problem("fast", 30, 22)
     lm = torch.tensor([1e-4], device=DEV)
