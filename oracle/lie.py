@@ -1,8 +1,9 @@
 """ORACLE (test infrastructure -- never imported by the product path).
 
-CPU restatement, in plain PyTorch (any float dtype, fp64 for pinning), of the SO3 / SE3 math of
+CPU restatement, in plain PyTorch (any float dtype, fp64 for pinning), of the SO3 / RxSO3 / SE3 / Sim3 math of
 the reference's lietorch:
-    forward formulas   dpvo/lietorch/include/so3.h:31-220, se3.h:36-217, common.h:7 (EPS = 1e-6)
+    forward formulas   dpvo/lietorch/include/so3.h:31-220, rxso3.h:11-324, se3.h:36-217, sim3.h:12-217,
+                       common.h:7 (EPS = 1e-6)
     backward formulas  dpvo/lietorch/src/lietorch_gpu.cu:32-256 (left-tangent-space gradients)
 
 The reference's native lietorch cannot be built here (Eigen 3.4.0 is not vendored and absent from
@@ -11,7 +12,8 @@ the image), so this restatement is pinned by the reference's own kn
 X * X^-1 = e, the adjoint identity, act == matrix action, and analytic-vs-numeric Jacobians of the
 composed backward operators.
 
-Layouts: SO3 [qx qy qz qw]; SE3 [tx ty tz qx qy qz qw]; tangents SO3 [phi], SE3 [tau, phi].
+Layouts: SO3 [qx qy qz qw]; RxSO3 [q, s]; SE3 [tx ty tz qx qy qz qw]; Sim3 [t, q, s];
+tangents SO3 [phi], RxSO3 [phi, sigma], SE3 [tau, phi], Sim3 [tau, phi, sigma].
 All functions take tensors of shape [..., dim] and broadcast over leading dims.
 """
 import math
@@ -287,6 +289,274 @@ def se3_projector(X):
     return J
 
 
+# ---------------------------------------------------------------------------------- RxSO3
+# data [qx qy qz qw s], tangent [phi, sigma]   (rxso3.h:11-324)
+def rxso3_split(X):
+    return q_normalize(X[..., :4]), X[..., 4:5]
+
+
+def rxso3_exp(a):
+    """rxso3.h:166-187: rotation as SO3::Exp, scale = exp(sigma)"""
+    return torch.cat([so3_exp(a[..., :3]), torch.exp(a[..., 3:4])], -1)
+
+
+def rxso3_log(X):
+    """rxso3.h:133-164"""
+    q, s = rxso3_split(X)
+    return torch.cat([so3_log(q), torch.log(s)], -1)
+
+
+def rxso3_inv(X):
+    q, s = rxso3_split(X)
+    return torch.cat([q_normalize(q_conj(q)), 1.0 / s], -1)
+
+
+def rxso3_mul(X, Y):
+    qx, sx = rxso3_split(X)
+    qy, sy = rxso3_split(Y)
+    return torch.cat([q_normalize(q_mul_raw(qx, qy)), sx * sy], -1)
+
+
+def rxso3_act(X, p):
+    q, s = rxso3_split(X)
+    return s * q_rot(q, p)
+
+
+def rxso3_Adj_matrix(X):
+    """rxso3.h:68-72: the scale commutes, so only the rotation acts on the tangent"""
+    q, _ = rxso3_split(X)
+    A = torch.zeros(X.shape[:-1] + (4, 4), dtype=X.dtype, device=X.device)
+    A[..., :3, :3] = q_matrix(q)
+    A[..., 3, 3] = 1
+    return A
+
+
+def rxso3_adj_small(a):
+    """rxso3.h:122-131"""
+    A = torch.zeros(a.shape[:-1] + (4, 4), dtype=a.dtype, device=a.device)
+    A[..., :3, :3] = hat(a[..., :3])
+    return A
+
+
+def rxso3_matrix(X):
+    q, s = rxso3_split(X)
+    T = torch.zeros(X.shape[:-1] + (4, 4), dtype=X.dtype, device=X.device)
+    T[..., :3, :3] = s[..., None] * q_matrix(q)
+    T[..., 3, 3] = 1
+    return T
+
+
+def rxso3_projector(X):
+    """rxso3.h:85-100 (5x5)"""
+    q, s = rxso3_split(X)
+    J = torch.zeros(X.shape[:-1] + (5, 5), dtype=X.dtype, device=X.device)
+    J[..., :4, :4] = so3_projector(q)
+    J[..., 3, 3] = 0                     # the SO3 block only fills rows 0..3 x cols 0..2
+    J[..., 4, 3] = s[..., 0]
+    return J
+
+
+def _blockdiag_so3(fn, a):
+    J = torch.zeros(a.shape[:-1] + (4, 4), dtype=a.dtype, device=a.device)
+    J[..., :3, :3] = fn(a[..., :3])
+    J[..., 3, 3] = 1
+    return J
+
+
+def rxso3_calcW(a):
+    """rxso3.h:189-234: W(phi, sigma) = A Phi + B Phi^2 + C I, with the small-angle / small-scale branches"""
+    phi, sigma = a[..., :3], a[..., 3]
+    th = phi.norm(dim=-1)
+    Phi = hat(phi)
+    Phi2 = Phi @ Phi
+    sc = torch.exp(sigma)
+    one = torch.ones_like(th)
+    s_small, t_small = sigma.abs() < EPS, th.abs() < EPS
+    ths = torch.where(t_small, one, th)
+    sgs = torch.where(s_small, one, sigma)
+    t2 = ths * ths
+    # sigma ~ 0
+    A0 = torch.where(t_small, 0.5 * one, (1.0 - torch.cos(ths)) / t2)
+    B0 = torch.where(t_small, one / 6.0, (ths - torch.sin(ths)) / (t2 * ths))
+    # general sigma
+    C1 = (sc - 1.0) / sgs
+    s2 = sgs * sgs
+    A1t = ((sgs - 1.0) * sc + 1.0) / s2
+    B1t = (sc * 0.5 * s2 + sc - 1.0 - sgs * sc) / (s2 * sgs)
+    sa, sb = sc * torch.sin(ths), sc * torch.cos(ths)
+    c = t2 + s2
+    A1g = (sa * sgs + (1.0 - sb) * ths) / (ths * c)
+    B1g = (C1 - ((sb - 1.0) * sgs + sa * ths) / c) / t2
+    A = torch.where(s_small, A0, torch.where(t_small, A1t, A1g))
+    B = torch.where(s_small, B0, torch.where(t_small, B1t, B1g))
+    C = torch.where(s_small, one, C1)
+    I = torch.eye(3, dtype=a.dtype, device=a.device)
+    return A[..., None, None] * Phi + B[..., None, None] * Phi2 + C[..., None, None] * I
+
+
+class _RxSO3:
+    N, K = 5, 4
+    exp = staticmethod(rxso3_exp)
+    log = staticmethod(rxso3_log)
+    inv = staticmethod(rxso3_inv)
+    mul = staticmethod(rxso3_mul)
+    act = staticmethod(rxso3_act)
+    act4 = staticmethod(lambda X, p: torch.cat([rxso3_act(X, p[..., :3]), p[..., 3:]], -1))
+    adj = staticmethod(lambda X, a: matv(rxso3_Adj_matrix(X), a))
+    adjT = staticmethod(lambda X, a: rowm(a, rxso3_Adj_matrix(X)))
+    Adj_matrix = staticmethod(rxso3_Adj_matrix)
+    adj_small = staticmethod(rxso3_adj_small)
+    left_jacobian = staticmethod(lambda a: _blockdiag_so3(so3_left_jacobian, a))            # rxso3.h:293-298
+    left_jacobian_inverse = staticmethod(lambda a: _blockdiag_so3(so3_left_jacobian_inverse, a))
+    projector = staticmethod(rxso3_projector)
+    matrix = staticmethod(rxso3_matrix)
+
+    @staticmethod
+    def act_jacobian(p):          # rxso3.h:307-311
+        return torch.cat([hat(-p), p[..., None]], -1)
+
+    @staticmethod
+    def act4_jacobian(p):         # rxso3.h:313-318
+        J = torch.zeros(p.shape[:-1] + (4, 4), dtype=p.dtype, device=p.device)
+        J[..., :3, :3] = hat(-p[..., :3])
+        J[..., :3, 3] = p[..., :3]
+        return J
+
+
+# ----------------------------------------------------------------------------------- Sim3
+# data [tx ty tz qx qy qz qw s], tangent [tau, phi, sigma]   (sim3.h:12-217)
+def sim3_split(X):
+    return X[..., :3], X[..., 3:8]
+
+
+def sim3_exp(a):
+    """sim3.h:160-167: t = W(phi, sigma) tau"""
+    return torch.cat([matv(rxso3_calcW(a[..., 3:7]), a[..., :3]), rxso3_exp(a[..., 3:7])], -1)
+
+
+def sim3_log(X):
+    """sim3.h:151-158: tau = W^-1 t (a general 3x3 inverse, as in the reference)"""
+    t, R = sim3_split(X)
+    ps = rxso3_log(R)
+    return torch.cat([matv(torch.linalg.inv(rxso3_calcW(ps)), t), ps], -1)
+
+
+def sim3_inv(X):
+    t, R = sim3_split(X)
+    Ri = rxso3_inv(R)
+    return torch.cat([-rxso3_act(Ri, t), Ri], -1)
+
+
+def sim3_mul(X, Y):
+    tx, Rx = sim3_split(X)
+    ty, Ry = sim3_split(Y)
+    return torch.cat([tx + rxso3_act(Rx, ty), rxso3_mul(Rx, Ry)], -1)
+
+
+def sim3_act(X, p):
+    t, R = sim3_split(X)
+    return rxso3_act(R, p) + t
+
+
+def sim3_act4(X, p):
+    t, R = sim3_split(X)
+    return torch.cat([rxso3_act(R, p[..., :3]) + p[..., 3:] * t, p[..., 3:]], -1)
+
+
+def sim3_matrix(X):
+    t, R = sim3_split(X)
+    T = rxso3_matrix(R)
+    T[..., :3, 3] = t
+    return T
+
+
+def sim3_Adj_matrix(X):
+    """sim3.h:98-110"""
+    t, R = sim3_split(X)
+    q, s = rxso3_split(R)
+    Rm = q_matrix(q)
+    A = torch.zeros(X.shape[:-1] + (7, 7), dtype=X.dtype, device=X.device)
+    A[..., :3, :3] = s[..., None] * Rm
+    A[..., :3, 3:6] = hat(t) @ Rm
+    A[..., :3, 6] = -t
+    A[..., 3:6, 3:6] = Rm
+    A[..., 6, 6] = 1
+    return A
+
+
+def sim3_adj_small(a):
+    """sim3.h:133-149"""
+    tau, phi, sigma = a[..., :3], a[..., 3:6], a[..., 6]
+    A = torch.zeros(a.shape[:-1] + (7, 7), dtype=a.dtype, device=a.device)
+    I = torch.eye(3, dtype=a.dtype, device=a.device)
+    A[..., :3, :3] = hat(phi) + sigma[..., None, None] * I
+    A[..., :3, 3:6] = hat(tau)
+    A[..., :3, 6] = -tau
+    A[..., 3:6, 3:6] = hat(phi)
+    return A
+
+
+def sim3_left_jacobian(a):
+    """sim3.h:169-180.  The reference's series stops at the Xi^4 / 120 term: the `+ Xi Xi^4 / 720` line follows a
+    semicolon and is dead code -- restated as it behaves."""
+    Xi = sim3_adj_small(a)
+    Xi2 = Xi @ Xi
+    Xi4 = Xi2 @ Xi2
+    I = torch.eye(7, dtype=a.dtype, device=a.device)
+    return I + Xi / 2.0 + Xi2 / 6.0 + (Xi @ Xi2) / 24.0 + Xi4 / 120.0
+
+
+def sim3_left_jacobian_inverse(a):
+    """sim3.h:182-191"""
+    Xi = sim3_adj_small(a)
+    Xi2 = Xi @ Xi
+    Xi4 = Xi2 @ Xi2
+    I = torch.eye(7, dtype=a.dtype, device=a.device)
+    return I - Xi / 2.0 + Xi2 / 12.0 - Xi4 / 720.0
+
+
+def sim3_projector(X):
+    """sim3.h:88-96 (8x8)"""
+    t, R = sim3_split(X)
+    J = torch.zeros(X.shape[:-1] + (8, 8), dtype=X.dtype, device=X.device)
+    J[..., :3, :3] = torch.eye(3, dtype=X.dtype, device=X.device)
+    J[..., :3, 3:6] = hat(-t)
+    J[..., :3, 6] = t
+    J[..., 3:, 3:] = rxso3_projector(R)
+    return J
+
+
+class _Sim3:
+    N, K = 8, 7
+    exp = staticmethod(sim3_exp)
+    log = staticmethod(sim3_log)
+    inv = staticmethod(sim3_inv)
+    mul = staticmethod(sim3_mul)
+    act = staticmethod(sim3_act)
+    act4 = staticmethod(sim3_act4)
+    adj = staticmethod(lambda X, a: matv(sim3_Adj_matrix(X), a))
+    adjT = staticmethod(lambda X, a: rowm(a, sim3_Adj_matrix(X)))
+    Adj_matrix = staticmethod(sim3_Adj_matrix)
+    adj_small = staticmethod(sim3_adj_small)
+    left_jacobian = staticmethod(sim3_left_jacobian)
+    left_jacobian_inverse = staticmethod(sim3_left_jacobian_inverse)
+    projector = staticmethod(sim3_projector)
+    matrix = staticmethod(sim3_matrix)
+
+    @staticmethod
+    def act_jacobian(p):          # sim3.h:193-199
+        I = torch.eye(3, dtype=p.dtype, device=p.device).expand(p.shape[:-1] + (3, 3))
+        return torch.cat([I, hat(-p), p[..., None]], -1)
+
+    @staticmethod
+    def act4_jacobian(p):         # sim3.h:201-207
+        J = torch.zeros(p.shape[:-1] + (4, 7), dtype=p.dtype, device=p.device)
+        J[..., :3, :3] = p[..., 3:, None] * torch.eye(3, dtype=p.dtype, device=p.device)
+        J[..., :3, 3:6] = hat(-p[..., :3])
+        J[..., :3, 6] = p[..., :3]
+        return J
+
+
 # --------------------------------------------------------------------- group-generic table
 class _SO3:
     N, K = 4, 3
@@ -354,7 +624,7 @@ class _SE3:
         return J
 
 
-GROUPS = {1: _SO3, 3: _SE3}
+GROUPS = {1: _SO3, 2: _RxSO3, 3: _SE3, 4: _Sim3}
 
 
 def _pad(g, G):

@@ -17,7 +17,7 @@ from oracle import lie as _L  # noqa: E402
 
 def _G(g):
     if g not in _L.GROUPS:
-        raise NotImplementedError("oracle lietorch_backends: group %d not restated (SO3=1, SE3=3 only)" % g)
+        raise NotImplementedError("oracle lietorch_backends: group %d not restated" % g)
     return _L.GROUPS[g]
 
 
