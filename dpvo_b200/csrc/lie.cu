@@ -1,11 +1,12 @@
-// lietorch_backends for sm_100a: SO3 and SE3, float and double, forward + backward.
+// lietorch_backends for sm_100a: SO3, RxSO3, SE3, Sim3, float and double, forward + backward.
 // Replaces dpvo/lietorch/src/lietorch_gpu.cu:20-601 (Eigen template kernels) with register math
 // from lie.cuh.  One group element per thread, grid-stride, outputs fully written (the reference
 // allocates with torch::zeros and overwrites; the unused last gradient component stays 0).
-// RxSO3 / Sim3 (group ids 2, 4) are not on the DPVO hot path; they return
-// DPVO_ERR_UNSUPPORTED.
+// SO3 / SE3 (the groups on the DPVO hot path) have hand-specialised operators below; RxSO3 / Sim3 (loop closure
+// only) run the generic small-matrix operators of lie_scaled.cuh.
 #include "common.cuh"
 #include "lie.cuh"
+#include "lie_scaled.cuh"
 
 namespace dpvo {
 using namespace lie;
@@ -201,14 +202,26 @@ __global__ void __launch_bounds__(256) lie_kernel(const LieArgs A) {
   }
 }
 
+// RxSO3 / Sim3: the generic operators (op codes of lie_scaled.cuh follow the enum above)
+template <int G, typename S, int OP>
+__global__ void __launch_bounds__(128) lie_scaled_kernel(const LieArgs A) {
+  static_assert((int)OP_JINV == (int)SOP_JINV && (int)OP_ACT4_B == (int)SOP_ACT4_B, "operator codes must match");
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (int64_t)gridDim.x * blockDim.x) {
+    if constexpr (G == DPVO_SIM3)
+      scaled_group_op<Sim3g<S>, S>(OP, (const S*)A.in0, (const S*)A.in1, (const S*)A.in2, (S*)A.out0, (S*)A.out1, (long long)i);
+    else
+      scaled_group_op<RxSO3g<S>, S>(OP, (const S*)A.in0, (const S*)A.in1, (const S*)A.in2, (S*)A.out0, (S*)A.out1, (long long)i);
+  }
+}
+
 template <int OP>
 static int lie_launch(int group, int dtype, const LieArgs& A, cudaStream_t st, const char* name) {
   if (A.n < 0) { set_error("%s: negative batch", name); return DPVO_ERR_INVALID; }
   if (A.n == 0) return DPVO_OK;
   if (!A.in0 || !A.out0) { set_error("%s: null pointer", name); return DPVO_ERR_INVALID; }
-  if (group != DPVO_SE3 && group != DPVO_SO3) {
-    set_error("%s: group %d (RxSO3/Sim3) is not built in this library", name, group);
-    return DPVO_ERR_UNSUPPORTED;
+  if (group != DPVO_SE3 && group != DPVO_SO3 && group != DPVO_RXSO3 && group != DPVO_SIM3) {
+    set_error("%s: unknown group id %d (SO3 = 1, RxSO3 = 2, SE3 = 3, Sim3 = 4)", name, group);
+    return DPVO_ERR_INVALID;
   }
   if (dtype != DPVO_F32 && dtype != DPVO_F64) {
     set_error("%s: dtype %d not supported (f32/f64)", name, dtype);
@@ -216,7 +229,16 @@ static int lie_launch(int group, int dtype, const LieArgs& A, cudaStream_t st, c
   }
   const int threads = 256;
   const unsigned blocks = (unsigned)std::min<int64_t>((A.n + threads - 1) / threads, (int64_t)sm_count() * 8);
-  if (group == DPVO_SE3) {
+  if (group == DPVO_RXSO3 || group == DPVO_SIM3) {
+    const unsigned sb = (unsigned)std::min<int64_t>((A.n + 127) / 128, (int64_t)sm_count() * 8);
+    if (group == DPVO_SIM3) {
+      if (dtype == DPVO_F32) lie_scaled_kernel<DPVO_SIM3, float, OP><<<sb, 128, 0, st>>>(A);
+      else lie_scaled_kernel<DPVO_SIM3, double, OP><<<sb, 128, 0, st>>>(A);
+    } else {
+      if (dtype == DPVO_F32) lie_scaled_kernel<DPVO_RXSO3, float, OP><<<sb, 128, 0, st>>>(A);
+      else lie_scaled_kernel<DPVO_RXSO3, double, OP><<<sb, 128, 0, st>>>(A);
+    }
+  } else if (group == DPVO_SE3) {
     if (dtype == DPVO_F32) lie_kernel<DPVO_SE3, float, OP><<<blocks, threads, 0, st>>>(A);
     else lie_kernel<DPVO_SE3, double, OP><<<blocks, threads, 0, st>>>(A);
   } else {

@@ -3,8 +3,8 @@
 Interface parity: dpvo/lietorch/groups.py:51-322 (LieGroup, SO3, SE3, cat, stack),
 group_ops.py:7-102 (autograd functions incl. ToVec / FromVec), broadcasting.py:9-31.
 Differences by design: operands are broadcast with expand (no physical repeat unless the kernel
-needs a contiguous copy), and only the groups on the DPVO hot path (SO3, SE3) are backed by
-kernels -- RxSO3 / Sim3 raise NotImplementedError.
+needs a contiguous copy); SO3 / SE3 (the groups on the DPVO hot path) run hand-specialised kernels, RxSO3 / Sim3
+the generic small-matrix operators of csrc/lie_scaled.cuh.
 """
 import numpy as np
 import torch
@@ -123,8 +123,6 @@ class LieGroup:
     # ---- op plumbing
     @classmethod
     def _apply(cls, fn, x, y=None):
-        if cls.group_id not in (1, 3):
-            raise NotImplementedError("%s is not backed by a kernel in dpvo_b200 (SO3 and SE3 are)" % cls.group_name)
         flat, lead = _flatten_pair(x, y)
         out = fn(cls.group_id, *flat)
         return out.view(lead + out.shape[1:])

@@ -250,7 +250,9 @@ int dpvo_reproject(const float* poses, const float* patches, const float* intrin
  * dtype = DPVO_F32 / DPVO_F64, n = batch (number of group elements), all tensors contiguous
  * [n, dim].  Embedding widths: SO3 4, RxSO3 5, SE3 7, Sim3 8; tangent widths 3, 4, 6, 7.
  * Backward functions follow lietorch_gpu.cu:32-256 (left-tangent gradients; gradients w.r.t.
- * group elements have the embedding width with the last component 0).
+ * group elements have the embedding width with the components past the tangent width 0).
+ * All four groups are implemented: SO3 / SE3 with register-specialised operators, RxSO3 / Sim3 (rxso3.h, sim3.h) with the
+ * generic small-matrix operators of csrc/lie_scaled.cuh.
  */
 int dpvo_lie_exp(int group, int dtype, const void* a, void* X, int64_t n, void* stream);
 int dpvo_lie_exp_backward(int group, int dtype, const void* grad, const void* a, void* da,
