@@ -11,8 +11,14 @@ GPU (no collective on the data path): whole-job value = N * stream rate, scaling
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same step through the
 public API with the new frame coming from pinned host memory and poses/depths read back to the host.
-`roofline` is for the dominant kernel (correlation): algorithmic bytes (50,492 B/edge at
-fp16) / measured kernel time vs the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`roofline` is for the dominant kernel CLASS of the step, the update operator's dense layers
+(linear_f16_kernel, 15 launches): algorithmic FLOPs (5.396 MFLOP/edge) / the summed CUDA-event
+time of those launches in the eager pass, vs the measured sustained dense tensor peak in MEASURED_PEAKS.json.
+`roofline_corr` keeps the correlation kernel's numbers: algorithmic bytes/time (served mostly by L2, so NOT an
+HBM fraction) next to the DRAM and L2 bytes of one launch from the committed ncu capture.
+`reference_cuda` = the reference's OWN CUDA pipeline for the same update on the same state, timed in the same
+run (oracle/ref_pipeline.py:RefCudaStep: ref_cuda_corr x2 + stack, torch Update under autocast, ref_cuda_ba
+from oracle/_ref) -- the same-box denominator of north_star's ">= 5x the reference CUDA build".
 `--impl reference` times the reference's CPU path (oracle port of F.grid_sample correlation + PyTorch
 Update + dpvo/ba.py BA, BASELINE.json configs[0] style) on a bounded sample of the same workload.
 """
@@ -29,15 +35,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_EDGE_FP16 = 50492      # SURVEY 8(d), both pyramid levels, s = 2 bytes
-METRIC = "VO frames/sec of the update hot path (corr + update operator + BA per frame)"
+METRIC = "update-iterations/sec of the DPVO hot path (reproject + corr + update operator + 2 BA iterations; one update per frame in steady state)"
+FLOP_PER_EDGE = 2 * (882 * 384 + 16 * 384 * 384)      # the 17 dense layers of the update operator
 
 
 def peaks():
+    """(HBM GB/s, dense 16-bit TFLOP/s sustained, source).  Sustained, not burst: the kernels are timed inside a step."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        tf = d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1416.5))
+        return d.get("hbm_gbs", 6650.0), tf, "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1416.5, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -136,7 +145,7 @@ def cpu_reference_step_factory(config, sample_stride, threads):
     return step, E, st.E
 
 
-def cpu_reference_measure(config, steps, warmup, budget_s):
+def cpu_reference_measure(config, steps, warmup, budget_s, full_check=False):
     """Times the CPU implementation of the update on a bounded sample; returns (frames/s scaled to the full graph,
     threads used, sample description, E_full).  The per-step sample is sized so that warmup + steps take about
     `budget_s` on this host: the cost of one step is probed on a thin sample first (cost is linear in the edges)."""
@@ -168,7 +177,16 @@ def cpu_reference_measure(config, steps, warmup, budget_s):
     dt = (time.perf_counter() - t0) / steps
     full = dt * Ef / Es                      # seconds per full update, linear in the edge count
     sample = "edges of every %dth patch: %d of %d edges per step, time scaled by %d/%d" % (stride, Es, Ef, Ef, Es)
-    return 1.0 / full, threads, sample, Ef
+    check = None
+    if full_check and stride > 1:
+        # ONE update on the whole graph (no sampling), to show what the scaling is worth: BA and the grouped
+        # softmax are not strictly linear in the edges
+        fstep, _, _ = cpu_reference_step_factory(config, 1, threads)
+        t0 = time.perf_counter(); fstep(); t_full = time.perf_counter() - t0
+        check = {"full_graph_one_step_s": t_full, "scaled_sample_s": full, "ratio": t_full / full}
+        full = t_full                        # the measured full-graph time is the number reported
+        sample += "; plus ONE untimed-loop step on all %d edges: %.2f s measured vs %.2f s scaled (reported value = measured full-graph step)" % (Ef, t_full, check["scaled_sample_s"])
+    return 1.0 / full, threads, sample, Ef, dt, check
 
 
 def run_reference(args):
@@ -176,9 +194,11 @@ def run_reference(args):
     if rank != 0:
         return
     # all host cores serve one stream at a time: the whole-job CPU rate does not grow with --gpus
-    val, threads, sample, Ef = cpu_reference_measure(args.config, args.steps, args.warmup, 120.0)
+    val, threads, sample, Ef, dt, check = cpu_reference_measure(args.config, args.steps, args.warmup, 100.0, full_check=True)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+           "ms_per_step_is": "measured wall time of one SAMPLED step (see cpu_baseline.sample); value = full-graph updates/s",
+           "full_graph_check": check, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": workload_config(args.config, Ef),
            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
@@ -186,19 +206,63 @@ def run_reference(args):
     print(json.dumps(out))
 
 
-def corr_dram_traffic():
-    """DRAM bytes of one correlation launch from the committed `ncu --set full` capture (profiles/), or None"""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_corr_fwd_tc.json")
+def _bytes(txt):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    val, unit = txt.split()
+    return float(val) * scale[unit]
+
+
+def ncu_summaries():
+    """hardware counters of the committed `ncu --set full` captures (profiles/): newest round first"""
+    out = {}
+    prof = os.path.join(ROOT, "profiles")
+    for rnd in ("r02", "r01"):
+        path = os.path.join(prof, "%s_ncu_corr_fwd_tc.json" % rnd)
+        if "corr_dram_bytes" not in out and os.path.exists(path):
+            try:
+                k = json.load(open(path))["kernels"][0]
+                out["corr_dram_bytes"] = _bytes(k["dram_read"]) + _bytes(k["dram_write"])
+                out["corr_l2_bytes"] = _bytes(k["l2_to_sm_read"]) if "l2_to_sm_read" in k else None
+                out["corr_source"] = "profiles/" + os.path.basename(path)
+            except Exception:
+                pass
+        path = os.path.join(prof, "%s_ncu_gemm_step.json" % rnd)
+        if "gemm_dram_bytes" not in out and os.path.exists(path):
+            try:
+                out["gemm_dram_bytes"] = sum(_bytes(k["dram_read"]) + _bytes(k["dram_write"]) for k in json.load(open(path))["kernels"])
+            except Exception:
+                pass
+    return out
+
+
+def reference_cuda_leg(st, run, our_ms, iters=10, warmup=3):
+    """The reference's own CUDA pipeline for the SAME update on the SAME state, timed here with CUDA events:
+    ref_cuda_corr.forward x2 + stack (dpvo.py:200-207), the torch Update under autocast (dpvo.py:332) with the same
+    weights, ref_cuda_ba.forward (2 iterations) -- oracle/ref_pipeline.py:RefCudaStep over oracle/_ref.  This is the
+    checker used as a baseline (allowed for bench.py); none of our kernels run inside it."""
+    import torch
     try:
-        k = json.load(open(path))["kernels"][0]
-        tot = 0.0
-        for key in ("dram_read", "dram_write"):
-            val, unit = k[key].split()
-            tot += float(val) * scale[unit]
-        return tot
-    except Exception:
-        return None
+        from oracle import update as OU
+        from oracle.ref_pipeline import RefCudaStep
+        mod = OU.Update(3).to(st.poses.device).eval()
+        mod.load_state_dict(run.update.state_dict())
+        ref = RefCudaStep(st, mod)
+    except Exception as exc:                               # noqa: BLE001 -- oracle/_ref not shipped: say so
+        return {"unavailable": str(exc).splitlines()[0][:160]}
+    for _ in range(warmup):
+        ref.reset(); ref.step()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        ref.reset()
+        ref.step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    return {"ms_per_step": ms, "value": 1e3 / ms, "unit": "frames/s", "iters": iters, "speedup_ours": ms / our_ms,
+            "what": "reference CUDA kernels (oracle/_ref: correlation_kernel.cu, ba_cuda.cu compiled for sm_100a) + torch Update under "
+                    "autocast, eager launches as in dpvo.py:328-360, same synthetic state and weights, same GPU, same process"}
 
 
 def workload_config(config, E):
@@ -224,7 +288,7 @@ def run_ours(args):
 
     n_frames = 36 if args.config == "default" else 30
     st = synthetic.make_state(args.config, n_frames, device=dev, seed=1234 + rank)
-    run = UpdateRunner(st, gemm=args.gemm)
+    run = UpdateRunner(st)
     E = st.E
 
     def barrier():
@@ -247,6 +311,8 @@ def run_ours(args):
     w0 = time.time()
     l0 = ex.launch_count()
     t_start.record()
+    gemm_events = []
+    run.update.gemm_events = gemm_events                 # (start, end) CUDA events around every dense-layer launch
     for i in range(args.steps):
         run.timers = {k: v[i] for k, v in ev.items()}
         run.reset()
@@ -256,6 +322,9 @@ def run_ours(args):
     windows.append((w0, time.time()))
     launches = ex.launch_count() - l0
     run.timers = None
+    run.update.gemm_events = None
+    gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events) / args.steps
+    gemm_launches = len(gemm_events) // args.steps
     ms_eager = t_start.elapsed_time(t_end) / args.steps
     ms = ms_eager
     corr_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(ev["corr0"], ev["corr1"]))
@@ -327,30 +396,44 @@ def run_ours(args):
     e2e_ms = e0.elapsed_time(e1) / args.steps
 
     # one stream per rank: whole-job rate = (steps of all ranks) / (slowest rank's time)
-    ms, e2e_ms, corr_ms, ba_ms = multigpu.max_over_ranks([ms, e2e_ms, corr_ms, ba_ms], dev)
+    ms, e2e_ms, corr_ms, ba_ms, gemm_ms = multigpu.max_over_ranks([ms, e2e_ms, corr_ms, ba_ms, gemm_ms], dev)
     if rank != 0:
         multigpu.finalize()
         return
 
-    hbm, which = peaks()
-    ach = BYTES_PER_EDGE_FP16 * E / (corr_ms * 1e-3) / 1e9
+    hbm, tensor_tf, which = peaks()
+    corr_alg = BYTES_PER_EDGE_FP16 * E / (corr_ms * 1e-3) / 1e9
+    # dense layers: 17 layers x E rows (+ the two h layers on the group rows, < 1 % and not counted)
+    gemm_flop = FLOP_PER_EDGE * E
+    gemm_tf = gemm_flop / (gemm_ms * 1e-3) / 1e12
+    ncu = ncu_summaries()
     out = {"metric": METRIC, "value": world * 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f16 operands, f32 accumulate/state (BA f32)", "data": "synthetic", "config": workload_config(args.config, E),
-           "breakdown_ms": {"corr": corr_ms, "ba": ba_ms, "update_op_and_rest": ms_eager - corr_ms - ba_ms, "gemm_backend": args.gemm,
-                            "eager_ms_per_step": ms_eager, "launch": launch_mode},
+           "breakdown_ms": {"corr": corr_ms, "ba": ba_ms, "dense_layers": gemm_ms, "dense_layer_launches": gemm_launches,
+                            "row_kernels_grouping_and_rest": ms_eager - corr_ms - ba_ms - gemm_ms,
+                            "gemm_backend": "tcgen05 (dpvo_linear_f16)", "eager_ms_per_step": ms_eager, "launch": launch_mode},
            "e2e": {"value": world * 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "pipeline": "frame t+1: pinned host -> staging on a copy stream while update t runs; staging -> ring slots, update (CUDA graph), "
                                "D2H of poses + depths and a stream synchronize per frame on the compute stream"},
            "gpu_launches": int(launches), "clocks": clocks,
-           "roofline": {"kernel": "corr_fwd_tc (2-level patch correlation, tcgen05 + TMA)", "bound": "hbm", "achieved": ach, "peak": hbm,
-                        "unit": "GB/s", "frac": ach / hbm, "traffic": corr_dram_traffic() if args.config == "default" else None,
-                        "traffic_note": "DRAM read+write bytes of one launch, ncu --set full capture committed under profiles/ "
-                                        "(L2 reuse of the feature ring keeps it below the algorithmic bytes, so frac can exceed 1)",
-                        "peak_source": which,
-                        "algorithmic_bytes_per_launch": BYTES_PER_EDGE_FP16 * E, "kernel_ms": corr_ms}}
+           "roofline": {"kernel": "linear_f16_kernel x%d (dense layers of the update operator, tcgen05.mma + TMA + TMEM)" % gemm_launches,
+                        "bound": "tensor", "achieved": gemm_tf, "peak": tensor_tf, "unit": "TFLOP/s", "frac": gemm_tf / tensor_tf,
+                        "traffic": ncu.get("gemm_dram_bytes"), "peak_source": which + ", sustained dense 16-bit (kernels timed inside a step)",
+                        "algorithmic_flop_per_step": gemm_flop, "kernel_ms": gemm_ms,
+                        "timing": "sum of CUDA-event intervals around each of the launches, eager pass, same stream",
+                        "traffic_note": "sum of dram__bytes_read+write over the dense-layer launches of one update, ncu capture under profiles/ (null until captured for this build)"},
+           "roofline_corr": {"kernel": "corr_fwd_tc (2-level patch correlation, tcgen05 + TMA)", "kernel_ms": corr_ms,
+                             "algorithmic_bytes_per_launch": BYTES_PER_EDGE_FP16 * E, "algorithmic_GBps": corr_alg,
+                             "note": "SURVEY 8(d)'s per-edge window bytes are served by L2 (each frame is reused ~11x), so algorithmic/HBM-peak (%.2f) is "
+                                     "NOT a DRAM fraction; the hardware counters of one launch are below" % (corr_alg / hbm),
+                             "dram_bytes": ncu.get("corr_dram_bytes"), "l2_to_sm_bytes": ncu.get("corr_l2_bytes"),
+                             "dram_frac_of_hbm_peak": (ncu["corr_dram_bytes"] / (corr_ms * 1e-3) / 1e9 / hbm) if ncu.get("corr_dram_bytes") else None,
+                             "ncu_source": ncu.get("corr_source")}}
+    if not args.no_reference_cuda and world == 1:
+        out["reference_cuda"] = reference_cuda_leg(st, run, ms)
     if not args.no_cpu_baseline and world == 1:          # the CPU leg is timed at N = 1 only
-        val, threads, sample, _ = cpu_reference_measure(args.config, 2, 1, 20.0)
+        val, threads, sample, _, _, _ = cpu_reference_measure(args.config, 2, 1, 20.0)
         out["cpu_baseline"] = {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample}
     print(json.dumps(out))
     multigpu.finalize()
@@ -363,8 +446,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="default", choices=["default", "fast"])
-    ap.add_argument("--gemm", default="tcgen05", choices=["cublas", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip the reference-CUDA-pipeline leg")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
     args = ap.parse_args()
     if args.steps is None:

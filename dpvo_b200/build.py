@@ -29,6 +29,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
 ]
+# perf-attribution switches (timestamps, dropped loads/stores, alternative code paths selected by environment
+# variables) exist only in builds made with DPVO_B200_PERF_EXPERIMENTS=1 (tools/); the release library has none
+if os.environ.get("DPVO_B200_PERF_EXPERIMENTS"):
+    NVCC_FLAGS.append("-DDPVO_B200_PERF_EXPERIMENTS")
 
 
 def _nvcc():

@@ -803,15 +803,18 @@ extern "C" int64_t dpvo_ba_workspace_bytes(int64_t E, int n_free_poses) {
 }
 
 static int ba_run(BaArgs& a, int iterations, cudaStream_t st) {
+#ifdef DPVO_B200_PERF_EXPERIMENTS
   static long long* dbg = nullptr;
   const bool timing = getenv("DPVO_B200_BA_TIMING") != nullptr;
   if (timing && !dbg) cudaMalloc(&dbg, 16 * sizeof(long long));
   a.dbg = timing ? dbg : nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
+#else
+  const bool timing = false;
+  a.dbg = nullptr;
+#endif
+  {   // per-device function attribute: set on every call (a process-wide flag would miss the second GPU)
     cudaError_t e = cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveSmem));
     if (e != cudaSuccess) return check_cuda(e, "ba_forward: cudaFuncSetAttribute");
-    attr_set = true;
   }
   const int red_blocks = sm_count() * 4;
   for (int it = 0; it < iterations; ++it) {
@@ -820,6 +823,7 @@ static int ba_run(BaArgs& a, int iterations, cudaStream_t st) {
     ba_solve_kernel<<<BA_CLUSTER, BA_SOLVE_THREADS, sizeof(SolveSmem), st>>>(a);
     DPVO_LAUNCH_CHECK("ba_solve_kernel");
   }
+#ifdef DPVO_B200_PERF_EXPERIMENTS
   if (timing) {
     long long h[16];
     cudaStreamSynchronize(st);
@@ -830,6 +834,9 @@ static int ba_run(BaArgs& a, int iterations, cudaStream_t st) {
     fprintf(stderr, " total=%lld | schur detail: setup %lld, first chunk staged %lld, chunk 1: multiply %lld, stage next + barrier %lld\n", h[10] - h[0],
             h[11] - h[0], h[12] - h[11], h[14] - h[13], h[15] - h[14]);
   }
+#else
+  (void)timing;
+#endif
   return DPVO_OK;
 }
 

@@ -698,11 +698,10 @@ static int launch_mma(const CorrArgs& a, bool pair_out, cudaStream_t st) {
   // list mode: the length lives on the device; one CTA per SM drains it
   const int64_t grid = std::min<int64_t>(need, (int64_t)sm_count() * (a.list ? 1 : 2));
   const size_t smem = sizeof(MmaWarpSmem) * MMA_WARPS;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(corr_fwd_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(corr_fwd_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
+  {   // per-device function attribute: set on every call
+    cudaError_t e = pair_out ? cudaFuncSetAttribute(corr_fwd_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(corr_fwd_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "corr_forward: cudaFuncSetAttribute");
   }
   if (pair_out) corr_fwd_mma<true><<<(unsigned)grid, MMA_WARPS * 32, smem, st>>>(a);
   else corr_fwd_mma<false><<<(unsigned)grid, MMA_WARPS * 32, smem, st>>>(a);
@@ -731,7 +730,7 @@ int corr_launch_fallback_list(const void* fmap1, const int64_t* s1, const void* 
 }
 
 static int corr_dispatch(const CorrArgs& a, int dtype, bool pair_out, cudaStream_t st) {
-  if (mma_eligible(a, dtype) && !getenv("DPVO_B200_CORR_GENERIC")) return launch_mma(a, pair_out, st);
+  if (mma_eligible(a, dtype)) return launch_mma(a, pair_out, st);
   switch (dtype) {
     case DPVO_F16: return launch_generic<__half>(a, st);
     case DPVO_BF16: return launch_generic<__nv_bfloat16>(a, st);
@@ -796,7 +795,7 @@ extern "C" int dpvo_corr_forward_pyramid2(const void* fmap1, const int64_t* fmap
   a.out_row = out_row_stride;
   // tcgen05 + TMA path: fp16 channels-last rings, batch 1, caller-provided scratch for the edge list
   if (workspace && workspace_bytes >= dpvo_corr_pyramid2_workspace_bytes(M) && B == 1 && S1 > 0 && S2 > 0 &&
-      mma_eligible(a, dtype) && !getenv("DPVO_B200_CORR_GENERIC") && !getenv("DPVO_B200_CORR_MMA")) {
+      mma_eligible(a, dtype)) {
     const int rc = corr_tc_forward(fmap1, a.s1, S1, fmap2_l0, a.s2[0], H0, W0, fmap2_l1, a.s2[1], H1, W1, S2, lvl1_div, coords, ii, jj,
                                    out, out_row_stride, M, workspace, (cudaStream_t)stream);
     if (rc != DPVO_ERR_UNSUPPORTED) return rc;

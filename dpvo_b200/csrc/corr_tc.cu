@@ -427,15 +427,12 @@ int corr_tc_forward(const void* fmap1, const int64_t* s1, int S1, const void* l0
     cache.key = key;
     cache.valid = true;
   }
-  static bool attr = false;
   const size_t smem = corr_tc_smem_bytes();
-  if (!attr) {
-    if (cudaFuncSetAttribute(corr_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(corr_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      cudaGetLastError();
-      return DPVO_ERR_UNSUPPORTED;
-    }
-    attr = true;
+  // per-device function attribute: set on every call
+  if (cudaFuncSetAttribute(corr_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaFuncSetAttribute(corr_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return DPVO_ERR_UNSUPPORTED;
   }
   int* fb = reinterpret_cast<int*>(scratch);
   int rc = check_cuda(cudaMemsetAsync(fb, 0, sizeof(int), st), "corr_tc: memset");

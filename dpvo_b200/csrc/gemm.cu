@@ -86,6 +86,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
 __device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
 }
+// 2-D TMA tile store smem -> global (SASS: UTMASTG), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tmap), "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -139,12 +147,19 @@ struct GemmBars {
 // delivers per SM; with W resident it is 43 B/clk/SM.
 // debug timestamps: dbg[role * 16 + tile] for the first 16 tiles of CTA 0.  roles: 0 MMA tile begin, 1 MMA accumulator
 // stage free, 2 MMA tile issued, 3 epilogue accumulator ready, 4 epilogue tile done, 5 kernel begin / weights landed
+#ifdef DPVO_B200_PERF_EXPERIMENTS
 #define GM_STAMP(role, t) do { if (a.dbg && blockIdx.x == 0 && lane == 0 && (t) < 16) a.dbg[(role) * 16 + (t)] = clock64(); } while (0)
+#define GM_EXP(bit) (a.exp_flags & (bit))
+#else
+#define GM_STAMP(role, t) do { } while (0)
+#define GM_EXP(bit) false
+#endif
 
 template <bool GATHER, bool WS, int EPI, int OUT>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmG, const GemmArgs a) {
+                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmG,
+                  const __grid_constant__ CUtensorMap tmY, const GemmArgs a) {
   extern __shared__ unsigned char gm_smem_raw[];
   constexpr int NST = WS ? GM_WS_ASTAGES : GM_STAGES;
   // 1024-byte alignment by pointer arithmetic on the shared array (an integer round trip would demote every
@@ -324,6 +339,76 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // lane = (row, 4 consecutive columns): 8 rows x 64 contiguous bytes per instruction.
     uint32_t tcount = 0;
     const int quarter = warp & 3, half = warp >> 2;
+    if constexpr (OUT == GM_OUT_F16 && EPI != DPVO_EPI_RESADD && EPI != DPVO_EPI_GATEDRES) {
+      // ---- fp16 result without epilogue operands: TMEM -> registers -> shared -> TMA store --------------------
+      // Every lane owns one accumulator row (the TMEM layout as it is): 32 columns at a time are biased / activated
+      // / packed in registers and written as four 16-byte chunks into a 32 x 32 fp16 staging tile in the
+      // SWIZZLE_64B pattern of the result's tensor map (chunk ^ ((row >> 1) & 3): the eight lanes of a
+      // shared-memory wavefront hit eight different 16-byte slots), and one lane hands the tile to the TMA unit.
+      // No transposition round trip, no per-lane global addressing, no LSU wavefronts for the result: the
+      // epilogue of a 128 x 192 tile dropped from ~4.7 k to the ~1 k cycles the MMAs of the next tile hide.
+      unsigned char* stile = sStage + warp * (GM_STG_FLOATS * 4);          // 2 KB per warp, 1024-byte aligned base
+      const uint32_t stile_u = smem_u32(stile);
+      const uint32_t my_row = stile_u + lane * 64;
+      const int sw = (lane >> 1) & 3;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        const int m0 = (int)((tile / n_tiles_n) * GM_M) + quarter * 32;
+        const int n0 = (int)(tile % n_tiles_n) * GM_N + half * (GM_N / 2);
+        const int nch = min(GM_N / 2 / 32, max(0, (a.N - n0) / 32));       // valid 32-column chunks (N % 32 == 0)
+        mbar_wait(&bars->tmem_full[acc], aph);
+        tc_fence_after();
+        GM_STAMP(3, tcount);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GM_N + half * (GM_N / 2);
+        uint32_t r[32];
+        if (nch > 0) tc_ld32(taddr, r);
+        else { tc_fence_before(); mbar_arrive(&bars->tmem_empty[acc]); }
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          const int col0 = n0 + c * 32;
+          float4 bv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)                                     // same address in every lane: one broadcast wavefront each
+            bv[j] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          tc_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] = __uint_as_float(r[4 * j]) + bv[j].x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bv[j].y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bv[j].z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bv[j].w;
+          }
+          if (c + 1 < nch) tc_ld32(taddr + (c + 1) * 32, r);
+          else { tc_fence_before(); mbar_arrive(&bars->tmem_empty[acc]); }     // last read of this accumulator stage
+          bool sig = EPI == DPVO_EPI_SIGMOID, relu = EPI == DPVO_EPI_RELU;
+          if constexpr (EPI == DPVO_EPI_SIGMOID_RELU) { sig = col0 < (a.N >> 1); relu = !sig; }   // uniform over the chunk
+          if (sig) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+          } else if (relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          uint4 o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<__half2*>(&o[j].x) = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
+            *reinterpret_cast<__half2*>(&o[j].y) = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+            *reinterpret_cast<__half2*>(&o[j].z) = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+            *reinterpret_cast<__half2*>(&o[j].w) = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+          }
+          if (lane == 0) bulk_wait_read<0>();                // the previous store has finished reading the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(my_row + ((j ^ sw) << 4)), "r"(o[j].x), "r"(o[j].y), "r"(o[j].z), "r"(o[j].w) : "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tmY, col0, m0, stile_u); bulk_commit(); }
+        }
+        GM_STAMP(4, tcount);
+      }
+      if (lane == 0) bulk_wait<0>();
+    } else {
     float4* stg = reinterpret_cast<float4*>(sStage) + warp * (GM_STG_FLOATS / 4);
     const int lrow = lane >> 2, lc4 = lane & 3;              // this lane's row (of 8) / 4-column chunk in the write-out
     constexpr bool fused = (EPI == DPVO_EPI_RESADD || EPI == DPVO_EPI_GATEDRES);
@@ -360,10 +445,10 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int it = 0; it < 4; ++it) {
             if (ok[it] && c < nch) {
               const char* p = rp + it * rstep + c * (res32 ? 64 : 32);
-              if (a.exp_flags & 1) rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (GM_EXP(1)) rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
               else if (res32) rv[it] = *reinterpret_cast<const float4*>(p);
               else { const uint2 q = *reinterpret_cast<const uint2*>(p); rv[it] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), 0.f, 0.f); }
-              if constexpr (EPI == DPVO_EPI_GATEDRES) gv[it] = (a.exp_flags & 2) ? make_uint2(0u, 0u) : *reinterpret_cast<const uint2*>(gp + it * gstep + c * 32);
+              if constexpr (EPI == DPVO_EPI_GATEDRES) gv[it] = GM_EXP(2) ? make_uint2(0u, 0u) : *reinterpret_cast<const uint2*>(gp + it * gstep + c * 32);
             }
           }
         }
@@ -446,11 +531,11 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(o4.x, o4.y);
           *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(o4.z, o4.w);
           if (ok[it]) {
-            if (!(a.exp_flags & 4)) {
+            if (!GM_EXP(4)) {
               if constexpr (OUT == GM_OUT_F16) *reinterpret_cast<uint2*>(yp + it * ystep + c * 32) = o;
               else *reinterpret_cast<float4*>(yp + it * ystep + c * 64) = o4;
             }
-            if constexpr (OUT == GM_OUT_F32_F16) { if (!(a.exp_flags & 8)) *reinterpret_cast<uint2*>(y16p + it * y16step + c * 32) = o; }
+            if constexpr (OUT == GM_OUT_F32_F16) { if (!GM_EXP(8)) *reinterpret_cast<uint2*>(y16p + it * y16step + c * 32) = o; }
           }
         }
       };
@@ -461,6 +546,7 @@ linear_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         chunk(c + 1, rvB, gvB, rvA, gvA);
       }
       GM_STAMP(4, tcount);
+    }
     }
   }
 
@@ -506,40 +592,55 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
   return DPVO_OK;
 }
 
+struct GemmMaps { CUtensorMap A, B, R, G, Y; };
+
 template <bool GATHER, bool WS, int EPI, int OUT>
-static int launch_out(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmG, const GemmArgs& a, unsigned grid, cudaStream_t st) {
+static int launch_out(const GemmMaps& m, const GemmArgs& a, unsigned grid, cudaStream_t st) {
   const size_t smem = (WS ? (size_t)GM_WS_ASTAGES * GM_A_BYTES + (size_t)GM_WS_MAXKB * GM_B_BYTES
                           : (size_t)GM_STAGES * (GM_A_BYTES + GM_B_BYTES)) + (size_t)GM_EPI_WARPS * GM_STG_FLOATS * 4 + sizeof(GemmBars) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(linear_f16_kernel<GATHER, WS, EPI, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return check_cuda(e, "linear_f16: cudaFuncSetAttribute");
-    attr = true;
-  }
-  linear_f16_kernel<GATHER, WS, EPI, OUT><<<grid, GM_THREADS, smem, st>>>(tmA, tmB, tmR, tmG, a);
+  // the opt-in is a per-device function attribute: set it on every launch (a cached flag would be wrong on the
+  // second GPU of a process and is not worth a lock)
+  cudaError_t e = cudaFuncSetAttribute(linear_f16_kernel<GATHER, WS, EPI, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return check_cuda(e, "linear_f16: cudaFuncSetAttribute");
+  linear_f16_kernel<GATHER, WS, EPI, OUT><<<grid, GM_THREADS, smem, st>>>(m.A, m.B, m.R, m.G, m.Y, a);
   DPVO_LAUNCH_CHECK("linear_f16_kernel");
   return DPVO_OK;
 }
 
 template <bool GATHER, bool WS, int EPI>
-static int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmG, const GemmArgs& a, unsigned grid, cudaStream_t st) {
-  if (a.y_dtype == DPVO_F16) return launch_out<GATHER, WS, EPI, GM_OUT_F16>(tmA, tmB, tmR, tmG, a, grid, st);
-  if (a.Y16) return launch_out<GATHER, WS, EPI, GM_OUT_F32_F16>(tmA, tmB, tmR, tmG, a, grid, st);
-  return launch_out<GATHER, WS, EPI, GM_OUT_F32>(tmA, tmB, tmR, tmG, a, grid, st);
+static int launch_epi(const GemmMaps& m, const GemmArgs& a, unsigned grid, cudaStream_t st) {
+  if (a.y_dtype == DPVO_F16) return launch_out<GATHER, WS, EPI, GM_OUT_F16>(m, a, grid, st);
+  if (a.Y16) return launch_out<GATHER, WS, EPI, GM_OUT_F32_F16>(m, a, grid, st);
+  return launch_out<GATHER, WS, EPI, GM_OUT_F32>(m, a, grid, st);
 }
 
 template <bool GATHER, bool WS>
-static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmG, const GemmArgs& a, unsigned grid, cudaStream_t st) {
+static int launch_variant(const GemmMaps& m, const GemmArgs& a, unsigned grid, cudaStream_t st) {
   switch (a.epilogue) {
-    case DPVO_EPI_NONE: return launch_epi<GATHER, WS, DPVO_EPI_NONE>(tmA, tmB, tmR, tmG, a, grid, st);
-    case DPVO_EPI_RELU: return launch_epi<GATHER, WS, DPVO_EPI_RELU>(tmA, tmB, tmR, tmG, a, grid, st);
-    case DPVO_EPI_SIGMOID: return launch_epi<GATHER, WS, DPVO_EPI_SIGMOID>(tmA, tmB, tmR, tmG, a, grid, st);
-    case DPVO_EPI_RESADD: return launch_epi<GATHER, WS, DPVO_EPI_RESADD>(tmA, tmB, tmR, tmG, a, grid, st);
-    case DPVO_EPI_SIGMOID_RELU: return launch_epi<GATHER, WS, DPVO_EPI_SIGMOID_RELU>(tmA, tmB, tmR, tmG, a, grid, st);
-    default: return launch_epi<GATHER, WS, DPVO_EPI_GATEDRES>(tmA, tmB, tmR, tmG, a, grid, st);
+    case DPVO_EPI_NONE: return launch_epi<GATHER, WS, DPVO_EPI_NONE>(m, a, grid, st);
+    case DPVO_EPI_RELU: return launch_epi<GATHER, WS, DPVO_EPI_RELU>(m, a, grid, st);
+    case DPVO_EPI_SIGMOID: return launch_epi<GATHER, WS, DPVO_EPI_SIGMOID>(m, a, grid, st);
+    case DPVO_EPI_RESADD: return launch_epi<GATHER, WS, DPVO_EPI_RESADD>(m, a, grid, st);
+    case DPVO_EPI_SIGMOID_RELU: return launch_epi<GATHER, WS, DPVO_EPI_SIGMOID_RELU>(m, a, grid, st);
+    default: return launch_epi<GATHER, WS, DPVO_EPI_GATEDRES>(m, a, grid, st);
   }
 }
 
+// fp16 result [rows, N], row stride ld: 32-row x 32-column store boxes in the SWIZZLE_64B pattern the epilogue writes
+static int make_store_tmap(CUtensorMap* m, void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) { set_error("linear_f16: cuTensorMapEncodeTiled is not available from the driver"); return DPVO_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("linear_f16: cuTensorMapEncodeTiled (result map) failed (%d)", (int)r); return DPVO_ERR_CUDA; }
+  return DPVO_OK;
+}
+
+#ifdef DPVO_B200_PERF_EXPERIMENTS
 // plain (unswizzled) 2-D map over an epilogue operand, used only for L2 prefetches of GM_M x GM_N tiles
 static bool make_prefetch_tmap(CUtensorMap* m, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn fn = encode_tiled();
@@ -553,28 +654,39 @@ static bool make_prefetch_tmap(CUtensorMap* m, const void* ptr, int dtype, int64
             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+#endif
 
 static int linear_launch(GemmArgs& a, cudaStream_t st) {
   const int n_tiles_n = (a.N + GM_N - 1) / GM_N;
   const int64_t tiles = ((a.rows + GM_M - 1) / GM_M) * n_tiles_n;
-  const bool ws = (a.K / GM_K) <= GM_WS_MAXKB && !getenv("DPVO_B200_GEMM_STREAM");
+  bool ws = (a.K / GM_K) <= GM_WS_MAXKB;
+#ifdef DPVO_B200_PERF_EXPERIMENTS
+  if (getenv("DPVO_B200_GEMM_STREAM")) ws = false;
+#endif
   // weight-stationary CTAs keep their column slice: the grid must be a multiple of the slice count
   int64_t grid = std::min<int64_t>(tiles, sm_count());
   if (ws) grid = std::max<int64_t>(n_tiles_n, grid / n_tiles_n * n_tiles_n);
-  CUtensorMap tmA, tmB, tmR, tmG;
-  memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB)); memset(&tmR, 0, sizeof(tmR)); memset(&tmG, 0, sizeof(tmG));
-  int rc = make_tmap(&tmB, a.W, a.N, a.K, a.ldw, GM_N);
+  GemmMaps m;
+  memset(&m, 0, sizeof(m));
+  int rc = make_tmap(&m.B, a.W, a.N, a.K, a.ldw, GM_N);
   if (rc) return rc;
   a.prefetch = 0;
-  if ((a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES) && getenv("DPVO_B200_GEMM_PREFETCH")) {
-    bool ok = make_prefetch_tmap(&tmR, a.res, a.res_dtype, a.rows, a.N, a.ldres);
-    if (ok && a.epilogue == DPVO_EPI_GATEDRES) ok = make_prefetch_tmap(&tmG, a.gate, DPVO_F16, a.rows, a.N, a.ldgate);
+  const bool fused = a.epilogue == DPVO_EPI_RESADD || a.epilogue == DPVO_EPI_GATEDRES;
+#ifdef DPVO_B200_PERF_EXPERIMENTS
+  if (fused && getenv("DPVO_B200_GEMM_PREFETCH")) {
+    bool ok = make_prefetch_tmap(&m.R, a.res, a.res_dtype, a.rows, a.N, a.ldres);
+    if (ok && a.epilogue == DPVO_EPI_GATEDRES) ok = make_prefetch_tmap(&m.G, a.gate, DPVO_F16, a.rows, a.N, a.ldgate);
     a.prefetch = ok ? 1 : 0;
   }
-  if (a.gather) return ws ? launch_variant<true, true>(tmA, tmB, tmR, tmG, a, (unsigned)grid, st) : launch_variant<true, false>(tmA, tmB, tmR, tmG, a, (unsigned)grid, st);
-  rc = make_tmap(&tmA, a.X, a.rows, a.K, a.ldx, GM_M);
+#endif
+  if (!fused && a.y_dtype == DPVO_F16) {                     // the result leaves through the TMA unit
+    rc = make_store_tmap(&m.Y, a.Y, a.rows, a.N, a.ldy);
+    if (rc) return rc;
+  }
+  if (a.gather) return ws ? launch_variant<true, true>(m, a, (unsigned)grid, st) : launch_variant<true, false>(m, a, (unsigned)grid, st);
+  rc = make_tmap(&m.A, a.X, a.rows, a.K, a.ldx, GM_M);
   if (rc) return rc;
-  return ws ? launch_variant<false, true>(tmA, tmB, tmR, tmG, a, (unsigned)grid, st) : launch_variant<false, false>(tmA, tmB, tmR, tmG, a, (unsigned)grid, st);
+  return ws ? launch_variant<false, true>(m, a, (unsigned)grid, st) : launch_variant<false, false>(m, a, (unsigned)grid, st);
 }
 
 extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather, const void* W, int64_t ldw,
@@ -609,6 +721,11 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
   a.Y16 = (__half*)Y16; a.ldy16 = ldy16;
   a.Y = Y; a.y_dtype = y_dtype; a.ldy = ldy; a.rows = rows; a.N = N; a.K = K; a.epilogue = epilogue;
 
+  a.dbg = nullptr;
+  a.exp_flags = 0;
+#ifdef DPVO_B200_PERF_EXPERIMENTS
+  // perf-attribution switches (tools/ only; never compiled into the release library): per-role timestamps of CTA 0
+  // and dropping operand loads / result stores
   static long long* dbg = nullptr;
   const bool timing = getenv("DPVO_B200_GEMM_TIMING") != nullptr;
   if (timing && !dbg) cudaMalloc(&dbg, 96 * sizeof(long long));
@@ -618,7 +735,9 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
     a.exp_flags = ex ? atoi(ex) : 0;
   }
   if (timing) cudaMemsetAsync(dbg, 0, 96 * sizeof(long long), (cudaStream_t)stream);
+#endif
   const int rc = linear_launch(a, (cudaStream_t)stream);
+#ifdef DPVO_B200_PERF_EXPERIMENTS
   if (timing && rc == DPVO_OK) {
     long long h[96];
     cudaStreamSynchronize((cudaStream_t)stream);
@@ -629,5 +748,6 @@ extern "C" int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather
       fprintf(stderr, "   tile %d: mma begin %lld  acc free %lld  issued %lld | epi ready %lld  done %lld\n", t, h[t] - t0, h[16 + t] - t0,
               h[32 + t] - t0, h[48 + t] - t0, h[64 + t] - t0);
   }
+#endif
   return rc;
 }

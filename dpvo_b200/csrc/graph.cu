@@ -366,12 +366,9 @@ static int group_launch_n(const GroupProblem* p0, const GroupProblem* p1, cudaSt
   if (p0->E == 0 && !two) return DPVO_OK;
   if (p0->E == 0) { a0 = a1; }                       // only the second problem has work: run it alone
   const bool both = two && p0->E > 0;
-  static int max_blocks = 0;
-  if (max_blocks == 0) {
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, group_edges_kernel, G_THREADS, 0);
-    max_blocks = std::max(1, per_sm) * sm_count();
-  }
+  int per_sm = 0;                                     // per device: asked on every call (host-side table lookup)
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, group_edges_kernel, G_THREADS, 0);
+  const int max_blocks = std::max(1, per_sm) * sm_count();
   // both y-slices use the same x extent; the tile loops stride by gridDim.x, so any extent >= 1 is correct
   const int want = both ? std::max(a0.ntiles, a1.ntiles) : a0.ntiles;
   const int grid = std::max(1, std::min(want, max_blocks / (both ? 2 : 1)));

@@ -469,6 +469,13 @@ Tensor softagg_reduce(Tensor fg, Tensor order, Tensor group_start, Tensor n_grou
   c10::cuda::CUDAGuard guard(fg.device());
   TORCH_CHECK(fg.scalar_type() == at::kHalf && fg.is_contiguous() && fg.size(-1) % 2 == 0, "softagg_reduce: expects contiguous float16 [E, 2*dim]");
   const int dim = fg.size(-1) / 2;
+  const int64_t E = fg.numel() / fg.size(-1);
+  TORCH_CHECK(order.is_cuda() && order.scalar_type() == at::kInt && order.is_contiguous() && order.numel() == E,
+              "softagg_reduce: order must be a contiguous int32 CUDA tensor with one entry per row of fg");
+  TORCH_CHECK(group_start.is_cuda() && group_start.scalar_type() == at::kInt && group_start.is_contiguous() && group_start.numel() >= max_groups + 1,
+              "softagg_reduce: group_start must be int32 with at least max_groups + 1 entries");
+  TORCH_CHECK(n_groups.is_cuda() && n_groups.scalar_type() == at::kInt && n_groups.numel() == 1, "softagg_reduce: n_groups must be a device int32 scalar");
+  TORCH_CHECK(max_groups >= 0 && max_groups <= E, "softagg_reduce: max_groups must be in [0, E]");
   Tensor y = torch::zeros({1, max_groups, dim}, fg.options());
   const at::Half* base = fg.data_ptr<at::Half>();
   check(dpvo_softagg_reduce(base, base + dim, 2 * dim, order.data_ptr<int>(), group_start.data_ptr<int>(),

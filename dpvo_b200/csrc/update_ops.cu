@@ -317,12 +317,10 @@ static int launch_ln_bulk(const void* a, const void* b, const void* c, int db, c
   constexpr int ES = (DA == DPVO_F32) ? 4 : 2;
   const size_t smem = (size_t)LNB_STAGES * LNB_ROWS * LNB_DIM * (ES + (HAS_C ? 2 : 0) + (b ? 2 : 0) + (cs ? 2 : 0)) + LNB_STAGES * sizeof(uint64_t) + 128;
   if (smem > LNB_SMEM_CAP) return DPVO_ERR_UNSUPPORTED;          // all four operands at once: the register kernel takes it
-  static bool attr = false;
-  if (!attr) {                                           // the largest layout (all four operands) of this instantiation
+  {                                                      // the largest layout (all four operands) of this instantiation; per device, every call
     const size_t smem_max = std::min<size_t>(LNB_SMEM_CAP, (size_t)LNB_STAGES * LNB_ROWS * LNB_DIM * (ES + (HAS_C ? 2 : 0) + 4) + LNB_STAGES * sizeof(uint64_t) + 128);
     cudaError_t e = cudaFuncSetAttribute(add_layernorm_bulk_kernel<DA, HAS_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return check_cuda(e, "add_layernorm: cudaFuncSetAttribute");
-    attr = true;
   }
   const int64_t n_tiles = (rows + LNB_ROWS - 1) / LNB_ROWS;
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(200 * 1024) / smem));
@@ -393,12 +391,12 @@ __global__ void __launch_bounds__(SA_SPLIT * SA_MAXPAIRS)
 softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ gl, int64_t ld,
                       const int32_t* __restrict__ order,
                       const int32_t* __restrict__ group_start, const int32_t* __restrict__ n_groups,
-                      __half* __restrict__ y, int dim) {
+                      __half* __restrict__ y, int dim, int max_groups) {
   constexpr int PF = 4;
   constexpr float LOG2E = 1.4426950408889634f;
   __shared__ __half2 s_max[SA_SPLIT][SA_MAXPAIRS];
   __shared__ float4 s_part[SA_SPLIT][SA_MAXPAIRS];
-  const int G = *n_groups;
+  const int G = min(*n_groups, max_groups);                  // y holds max_groups rows (host hint): never write past it
   const int npairs = blockDim.x / SA_SPLIT;                 // channel pairs handled per pass
   const int pr = threadIdx.x % npairs, sp = threadIdx.x / npairs;
   for (int g = blockIdx.x; g < G; g += gridDim.x) {
@@ -574,7 +572,7 @@ extern "C" int dpvo_add_layernorm(const void* a, const void* b, const void* c, c
   // the update operator's shapes (dim 384): fp16 alone, fp32 alone, fp32 + fp16 (+ fp16)
   const bool bc16 = (!b || db == DPVO_F16) && (!c || dc == DPVO_F16);
   // dim 384, dense 16-byte aligned rows: operands a and c staged through shared memory by bulk copies
-  if (nv == 3 && bc16 && ROW_WARPS * 2 == LNB_ROWS && !getenv("DPVO_B200_LN_REGISTER") && ((uintptr_t)a & 15) == 0 &&
+  if (nv == 3 && bc16 && ROW_WARPS * 2 == LNB_ROWS && ((uintptr_t)a & 15) == 0 &&
       (!c || ((uintptr_t)c & 15) == 0) && (!b || ((uintptr_t)b & 15) == 0) &&
       (!c_scale || (((uintptr_t)c_scale & 15) == 0 && (ld_c_scale * 2) % 16 == 0))) {
     int rc;
@@ -649,7 +647,7 @@ extern "C" int dpvo_softagg_reduce(const void* f16, const void* g16, int64_t ld,
   const int pairs = std::min(SA_MAXPAIRS, std::max(32, ((dim / 2 + 31) / 32) * 32));
   const int threads = pairs * SA_SPLIT;
   softagg_reduce_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)f16, (const __half*)g16, ld, order, group_start,
-                                                                   n_groups, (__half*)y16, dim);
+                                                                   n_groups, (__half*)y16, dim, (int)max_groups);
   DPVO_LAUNCH_CHECK("softagg_reduce_kernel");
   return DPVO_OK;
 }

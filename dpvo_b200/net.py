@@ -10,8 +10,8 @@ Data flow is fp32 for the carried state `net`, fp16 for every GEMM operand (what
 autocast does, dpvo.py:332), with the fp16 copies produced inside the fused row kernels.  The edge
 groupings come from ONE device radix-sort launch each (no host sync, no torch.unique, no D2H sort).
 
-Dense layers go through `dense()`: the tcgen05 kernel of include/dpvo_b200.h (dpvo_linear_f16) when
-`gemm="tcgen05"`, or cuBLAS via torch (`gemm="cublas"`, the library baseline kept for comparison).
+Every dense layer runs on the tcgen05 kernel of include/dpvo_b200.h (dpvo_linear_f16); there is no library
+GEMM and no other backend in the product (a cuBLAS comparison lives in tools/bench_gemm.py only).
 """
 import torch
 import torch.nn as nn
@@ -67,17 +67,25 @@ class EdgeGroups:
         if _fields is None:
             _fields = extensions()[3].group_edges(key_a, key_b, sec)
         self.order, self.group_of, self.group_start, self.key_a, self.key_b, self.n = _fields
+        # `max_groups` sizes the per-group buffers.  Callers that know a bound (UpdateRunner: patch slots, frame
+        # pairs) pass it and nothing ever leaves the device; without one the count is read back (one sync -- the
+        # reference's torch.unique in blocks.py:41 synchronises too).
         self.max_groups = int(self.n.item()) if max_groups is None else int(max_groups)
 
     @classmethod
     def pair(cls, spec0, spec1, max_groups0=None, max_groups1=None):
-        """both groupings of an update -- spec = (key_a, key_b, sec) -- in one cooperative launch"""
+        """both groupings of an update -- spec = (key_a, key_b, sec) -- in one cooperative launch; missing bounds
+        are read back together (a single device->host copy for both)"""
         f = extensions()[3].group_edges_pair(*spec0, *spec1)
+        if max_groups0 is None or max_groups1 is None:
+            n0, n1 = torch.stack([f[5].reshape(()), f[11].reshape(())]).tolist()
+            max_groups0 = n0 if max_groups0 is None else max_groups0
+            max_groups1 = n1 if max_groups1 is None else max_groups1
         return cls(None, max_groups=max_groups0, _fields=f[:6]), cls(None, max_groups=max_groups1, _fields=f[6:])
 
 
 class Update(nn.Module):
-    def __init__(self, p=3, gemm="cublas"):
+    def __init__(self, p=3):
         super().__init__()
         self.c1 = nn.Sequential(nn.Linear(DIM, DIM), nn.ReLU(inplace=True), nn.Linear(DIM, DIM))
         self.c2 = nn.Sequential(nn.Linear(DIM, DIM), nn.ReLU(inplace=True), nn.Linear(DIM, DIM))
@@ -90,14 +98,26 @@ class Update(nn.Module):
                                   nn.LayerNorm(DIM, eps=1e-3), nn.ReLU(inplace=True), nn.Linear(DIM, DIM))
         self.d = nn.Sequential(nn.ReLU(inplace=False), nn.Linear(DIM, 2), GradientClip())
         self.w = nn.Sequential(nn.ReLU(inplace=False), nn.Linear(DIM, 2), GradientClip(), nn.Sigmoid())
-        self.gemm = gemm
         self.inplace_state = False     # True: forward() overwrites an fp32 `net` argument with the new state
         self._packed = None
+        self._packed_key = None
+
+    # The packed fp16 copies follow the parameters: any in-place change (load_state_dict, an optimiser step) bumps
+    # the parameters' version counters, .to()/.cuda() replaces their storage -- both change this key.
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version, p.device) for p in self.parameters())
+
+    def packed(self):
+        key = self._param_key()
+        if self._packed is None or self._packed_key != key:
+            self.pack()
+            self._packed_key = key
+        return self._packed
 
     # ------------------------------------------------------------------ packed inference weights
     def pack(self):
-        """fp16 copies of the dense weights (+ fp32 biases) for the inference path; call again after
-        loading a checkpoint."""
+        """fp16 copies of the dense weights (+ fp32 biases) for the inference path (rebuilt by `packed()` whenever
+        the parameters changed)."""
         def lin(m):
             return (m.weight.detach().half().contiguous(), m.bias.detach().float().contiguous())
         P = {}
@@ -122,12 +142,6 @@ class Update(nn.Module):
         self._packed = P
         return P
 
-    def dense(self, x16, wb, relu=False):
-        """library baseline: cuBLAS through torch"""
-        w, b = wb
-        y = F.linear(x16, w, b.half())
-        return F.relu_(y) if relu else y
-
     # ------------------------------------------------------------------------------- forward
     @torch.no_grad()
     def forward(self, net, inp, corr, flow, ii, jj, kk, groups_kk=None, groups_ij=None, inp_index=None, coords=None):
@@ -141,26 +155,33 @@ class Update(nn.Module):
         if corr.shape[-1] != CORR_PAD:
             corr = F.pad(corr, (0, CORR_PAD - corr.shape[-1]))
         inp = inp if inp.dtype in (torch.half, torch.float32) else inp.half()
-        if groups_kk is None:
+        if groups_kk is None and groups_ij is None:
+            groups_kk, groups_ij = EdgeGroups.pair((kk, None, jj), (ii, jj, None))
+        elif groups_kk is None:
             groups_kk = EdgeGroups(kk, None, jj)
-        if groups_ij is None:
+        elif groups_ij is None:
             groups_ij = EdgeGroups(ii, jj, None)
-        if self.gemm == "tcgen05":
-            return self._forward_tcgen05(net, inp, corr, groups_kk, groups_ij)
-        if self.gemm == "cublas":
-            return self._forward_cublas(net, inp, corr, groups_kk, groups_ij)
-        raise RuntimeError("Update: unknown gemm backend %r" % self.gemm)
+        return self._forward_tcgen05(net, inp, corr, groups_kk, groups_ij)
 
     def _forward_tcgen05(self, net, inp, corr, groups_kk, groups_ij):
         """every dense layer on dpvo_linear_f16, with the gather / residual / gating fused into the
         operand load and the epilogue"""
         ex = extensions()[3]
-        P = self._packed or self.pack()
+        P = self.packed()
         NONE, RELU, SIGM, RESADD, GATED, SIGM_RELU = 0, 1, 2, 3, 4, 5
+
+        gev = getattr(self, "gemm_events", None)          # bench.py: CUDA events around every dense-layer launch
 
         def L(x, name, epi=NONE, **kw):
             wgt, b = P[name]
-            return ex.linear_f16(x, wgt, b, epi, **kw)
+            if gev is None:
+                return ex.linear_f16(x, wgt, b, epi, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = ex.linear_f16(x, wgt, b, epi, **kw)
+            e1.record()
+            gev.append((e0, e1))
+            return y
 
         h = L(L(corr, "corr0", RELU), "corr2")
         _, h = ex.add_layernorm(h, None, None, self.corr[3].weight, self.corr[3].bias, 1e-3, True, False, True)
@@ -190,31 +211,4 @@ class Update(nn.Module):
         ga = L(x16, "gr3_ga", SIGM_RELU)
         r2 = L(ga[..., DIM:], "gr3_b")
         delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"], self._coords, ga[..., :DIM], r2)    # x32 <- x32 + gate * res
-        return x32, (delta, weight, None)
-
-    def _forward_cublas(self, net, inp, corr, groups_kk, groups_ij):
-        ex = extensions()[3]
-        P = self._packed or self.pack()
-        h = self.dense(corr, P["corr0"], relu=True)
-        h = self.dense(h, P["corr2"])
-        _, h = ex.add_layernorm(h, None, None, self.corr[3].weight, self.corr[3].bias, 1e-3, True, False, True)
-        h = self.dense(h, P["corr5"])
-        net32, _ = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, False, self._inp_index)
-        ix, jx = ex.neighbors_from_groups(groups_kk.order, groups_kk.group_of)
-        n16 = None
-        for idx, a, b in ((ix, "c1a", "c1b"), (jx, "c2a", "c2b")):
-            g16 = ex.gather_rows_masked(net32, idx, True)
-            u = self.dense(self.dense(g16, P[a], relu=True), P[b])
-            n16 = ex.residual_add_(net32, u, None, idx is jx)
-        for grp, nm in ((groups_kk, "kk"), (groups_ij, "ij")):
-            fg = self.dense(n16, P["fg_" + nm])
-            y = ex.softagg_reduce(fg, grp.order, grp.group_start, grp.n, grp.max_groups)
-            n16 = ex.residual_add_(net32, self.dense(y, P["h_" + nm]), grp.group_of, True)
-        x32 = net32
-        for i, ln in ((1, self.gru[0]), (3, self.gru[2])):
-            x32, x16 = ex.add_layernorm(x32, None, None, ln.weight, ln.bias, 1e-3, False, True, True)
-            gate = self.dense(x16, P["gr%d_g" % i])
-            r2 = self.dense(self.dense(x16, P["gr%d_a" % i], relu=True), P["gr%d_b" % i])
-            x32, _ = ex.gated_residual(x32, gate, r2, False)
-        delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"], self._coords)
         return x32, (delta, weight, None)

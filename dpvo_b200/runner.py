@@ -16,16 +16,15 @@ from .net import Update, EdgeGroups, DIM
 
 
 class UpdateRunner:
-    def __init__(self, state, update=None, gemm="cublas", ba_iterations=2, seed=1234):
+    def __init__(self, state, update=None, ba_iterations=2, seed=1234):
         self.s = state
         dev = state.poses.device
         if update is None:
             torch.manual_seed(seed)                    # evaluate_tartan.py:173
-            update = Update(3, gemm=gemm)
+            update = Update(3)
         self.update = update.to(dev).eval()
-        self.update.gemm = gemm
         self.update.inplace_state = True               # `self.net` is one buffer, updated in place
-        self.update.pack()
+        self.update.packed()
         self.graph = None
         self.M = state.cfg["M"]
         self.mem = state.fmap1.shape[1]

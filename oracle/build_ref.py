@@ -16,6 +16,13 @@ lietorch_backends cannot be built (every kernel is Eigen template code): no _ref
 
 Outputs: oracle/_ref/ref_cuda_corr<EXT>, oracle/_ref/ref_cuda_ba<EXT> (module names prefixed so they
 can be imported next to ours).  git-ignored, not gpurun-ignored.  Run: python oracle/build_ref.py
+
+stage_python(): the reference's *Python* package (dpvo/*.py, altcorr/, fastba/, lietorch/ wrappers,
+config/*.yaml -- interpreted code, no build step) packed UNMODIFIED into oracle/_ref/dpvo_ref_py.zip so that the GPU
+box, where /root/reference does not exist, can run the reference's own host code (DPVO.update,
+net.Update, altcorr.corr, fastba.BA, lietorch/run_tests.py) on top of either set of native modules:
+ours (the drop-in being exercised) or oracle/_ref (the reference-CUDA arm of bench.py).  Same status
+as oracle/_ref: a build output of the checker, git-ignored, never part of the repository history.
 """
 import os
 import re
@@ -97,6 +104,33 @@ def build(force=False):
     return True
 
 
+PY_ZIP = os.path.join(OUT, "dpvo_ref_py.zip")
+_PY_SKIP = ("data_readers", "retrieval", "include", "src", "__pycache__")
+
+
+def stage_python(force=False):
+    """pack the reference's .py files (and the two yaml configs), byte for byte, into oracle/_ref/dpvo_ref_py.zip;
+    Python imports packages straight from a zip on sys.path, so nothing is ever unpacked into the tree"""
+    import zipfile
+    if not os.path.isdir(REF):
+        return os.path.exists(PY_ZIP)
+    if os.path.exists(PY_ZIP) and not force:
+        return True
+    os.makedirs(OUT, exist_ok=True)
+    with zipfile.ZipFile(PY_ZIP, "w", zipfile.ZIP_DEFLATED) as z:
+        for dirpath, dirnames, filenames in os.walk(REF):
+            dirnames[:] = sorted(d for d in dirnames if d not in _PY_SKIP)
+            rel = os.path.relpath(dirpath, os.path.dirname(REF))
+            z.writestr(rel + "/", b"")        # directory entry: dpvo/loop_closure has no __init__.py (namespace package)
+            for f in sorted(filenames):
+                if f.endswith(".py"):
+                    z.write(os.path.join(dirpath, f), os.path.join(rel, f))
+        for f in ("default.yaml", "fast.yaml"):
+            z.write(os.path.join(os.path.dirname(REF), "config", f), os.path.join("config", f))
+    return True
+
+
 if __name__ == "__main__":
+    stage_python(force="--force" in sys.argv)
     ok = build(force="--force" in sys.argv)
     print("oracle/_ref:", "built" if ok else "reference tree not mounted; skipped")

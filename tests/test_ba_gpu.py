@@ -81,11 +81,15 @@ def test_ba_is_deterministic(ext):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
-def test_ba_grouped_entry_is_bit_identical(ext):
-    """dpvo_ba_forward_grouped on groupings built by the caller == cuda_ba.forward (which builds them)"""
+@pytest.mark.parametrize("config,n_frames", [("fast", 30), ("default", 36)])
+def test_ba_grouped_entry_matches_plain_entry(ext, config, n_frames):
+    """dpvo_ba_forward_grouped on groupings built by the caller vs cuda_ba.forward (which builds them): the same
+    arithmetic on the same groups; the members of a kk group may arrive in another order (the caller's grouping
+    uses jj as a secondary key, cuda_ba.forward's does not), which moves fp32 sums by an ulp or two -- hence a
+    1e-5 relative bar rather than bit equality (two runs of either entry ARE bit-identical: test_ba_is_deterministic)"""
     from dpvo_b200.net import EdgeGroups
     from dpvo_b200 import fastba
-    st, target, weight = _problem("fast", 30, 27)
+    st, target, weight = _problem(config, n_frames, 27)
     lm = torch.tensor([1e-4], device=DEV)
     ii, jj, kk = st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV)
     p1, q1 = st.poses.clone().to(DEV)[None], st.patches.clone().to(DEV)[None]
@@ -95,7 +99,8 @@ def test_ba_grouped_entry_is_bit_identical(ext):
     gk, gp = EdgeGroups(kk, None, jj), EdgeGroups(ii, jj, None)       # kk groups may carry any member order
     fastba.BA_grouped(p2, q2, st.intrinsics.to(DEV)[None], target.to(DEV)[None], weight.to(DEV)[None], lm, ii, jj, kk,
                       st.t0, st.n, 2, gk, gp)
-    assert (p1 - p2).abs().max().item() < 1e-5 and (q1 - q2).abs().max().item() < 1e-5
+    live = st.kk.unique().to(DEV)
+    assert _rel(p2[0, :st.n], p1[0, :st.n]) < 1e-5 and _rel(q2[0, live, 2], q1[0, live, 2]) < 1e-5
 
 
 def test_ba_structure_only(ext):
@@ -133,7 +138,10 @@ def test_ba_outliers_and_clamps(ext):
     # the patches and bounded drift of the poses
     close = (d - r).abs() <= 1e-3 * r.abs() + 1e-6
     assert close.float().mean().item() > 0.99, close.float().mean().item()
-    assert (d == 1.0).any() or (r == 1.0).any() or True
+    # both clamp branches of ba_cuda.cu:218-221 were exercised by this problem, on the oracle and on the device
+    assert (r == 1.0).any() and (d == 1.0).any(), "no depth took the d > 20 -> 1.0 branch"
+    lo = float(torch.tensor(1e-4, dtype=torch.float32))
+    assert (r <= 1e-4 * (1 + 1e-6)).any() and (d == lo).any(), "no depth was clamped to 1e-4"
     assert (d >= float(torch.tensor(1e-4, dtype=torch.float32))).all() and (d <= 20.0).all()
     assert _rel(poses[0].cpu().double()[:st.n], rp[:st.n]) < 2e-2
 

@@ -21,6 +21,8 @@ def test_reference_arm_prints_one_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+    # ms_per_step is the measured time of one sampled step (what the driver multiplies by steps), not the scaled one
+    assert line["ms_per_step"] > 0 and "ms_per_step_is" in line
 
 
 def test_non_zero_ranks_of_the_reference_arm_stay_silent():
@@ -36,5 +38,9 @@ def test_roofline_traffic_comes_from_the_committed_capture():
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    t = mod.corr_dram_traffic()
+    n = mod.ncu_summaries()
+    t = n["corr_dram_bytes"]
     assert t is not None and 1e8 < t < mod.BYTES_PER_EDGE_FP16 * 47712       # DRAM bytes stay below the algorithmic bytes
+    assert n["corr_l2_bytes"] > t and n["corr_source"].startswith("profiles/")
+    hbm, tf, src = mod.peaks()
+    assert 1000 < hbm < 9000 and 500 < tf < 2500

@@ -190,3 +190,52 @@ def test_patchify_forward_backward(ext, radius, C):
     OC.patchify_raw(n, coords, radius).backward(grad)
     gout, = ext[0].patchify_backward(net.to(DEV), coords.to(DEV), grad.to(DEV), radius)
     assert (gout.cpu() - n.grad).abs().max().item() <= 1e-5
+
+
+# ---------------------------------------------------------------- host wrappers (dpvo_b200/altcorr.py) with autograd
+def test_altcorr_corr_autograd_with_dropout_matches_oracle(ext):
+    """altcorr.corr forward + backward through torch autograd, including the edge dropout drawn with torch.rand on
+    the CUDA generator inside backward (correlation.py:20-25): same seed -> same kept edges -> oracle gradient"""
+    from dpvo_b200 import altcorr
+    g = torch.Generator().manual_seed(171)
+    M, S1, S2, H, W = 90, 20, 3, 18, 22
+    f1 = torch.randn(1, S1, 128, 3, 3, generator=g) / 4
+    f2 = torch.randn(1, S2, 128, H, W, generator=g) / 4
+    coords = torch.zeros(1, M, 2, 3, 3)
+    offs = torch.arange(3).float() - 1
+    coords[0, :, 0] = (torch.rand(M, generator=g) * W)[:, None, None] + offs[None, None, :]
+    coords[0, :, 1] = (torch.rand(M, generator=g) * H)[:, None, None] + offs[None, :, None]
+    ii, jj = torch.randint(0, S1, (M,), generator=g), torch.randint(0, S2, (M,), generator=g)
+    grad = torch.randn(1, M, 7, 7, 3, 3, generator=g)
+    for dropout in (1, 0.5):
+        a = f1.to(DEV).requires_grad_(True)
+        b = f2.to(DEV).requires_grad_(True)
+        out = altcorr.corr(a, b, coords.to(DEV), ii.to(DEV), jj.to(DEV), 3, dropout)
+        torch.manual_seed(99)
+        out.backward(grad.to(DEV))
+        torch.manual_seed(99)
+        keep = (torch.rand(M, device=DEV) < dropout).cpu() if dropout < 1 else torch.ones(M, dtype=torch.bool)
+        a64, b64 = f1.double().requires_grad_(True), f2.double().requires_grad_(True)
+        ref = OC.corr_forward(a64, b64, coords, ii, jj, 3)
+        (ref * grad.double() * keep[None, :, None, None, None, None]).sum().backward()
+        assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-5 * ref.abs().max().item()
+        for mine, theirs in ((a.grad, a64.grad), (b.grad, b64.grad)):
+            assert (mine.cpu().double() - theirs).abs().max().item() <= 3e-5 * theirs.abs().max().item()
+
+
+def test_altcorr_patchify_bilinear_autograd_matches_oracle(ext):
+    from dpvo_b200 import altcorr
+    g = torch.Generator().manual_seed(172)
+    net = torch.randn(2, 24, 20, 28, generator=g)
+    coords = torch.stack([torch.rand(2, 30, generator=g) * 24 + 1.5, torch.rand(2, 30, generator=g) * 16 + 1.5], -1)
+    x = net.to(DEV).requires_grad_(True)
+    out = altcorr.patchify(x, coords.to(DEV), 1)
+    grad = torch.randn(out.shape, generator=g)
+    out.backward(grad.to(DEV))
+    x64 = net.double().requires_grad_(True)
+    ref = OC.patchify(x64, coords.double(), 1)
+    ref.backward(grad.double())
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() < 1e-5
+    assert (x.grad.cpu().double() - x64.grad).abs().max().item() < 1e-4
+    raw = altcorr.patchify(net.to(DEV), coords.to(DEV), 1, mode="nearest")
+    assert torch.equal(raw.cpu(), OC.patchify_raw(net, coords, 1))
