@@ -439,8 +439,93 @@ def run_ours(args):
     multigpu.finalize()
 
 
+# ------------------------------------------------------------------------------------ training step (configs[3])
+TRAIN_METRIC = ("training clips/sec: batch of 8 synthetic 15-frame 480x640 subsequences per optimiser step, 18 unrolled updates "
+                "(altcorr fwd+bwd, differentiable update operator and BA), NCCL gradient all-reduce, AdamW")
+
+
+def synthetic_clip(device, seed, n_frames=15, ht=480, wd=640):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    images = (torch.rand(1, n_frames, 3, ht, wd, generator=g, device=device) * 255).floor()
+    k = torch.ones(3, 1, 5, 5, device=device) / 25
+    images = torch.nn.functional.conv2d(images[0], k, padding=2, groups=3)[None]          # uint8-valued-ish smooth frames
+    disps = 0.1 + 0.9 * torch.rand(1, n_frames, ht, wd, generator=g, device=device)
+    poses = torch.zeros(1, n_frames, 7, device=device)
+    poses[..., 6] = 1.0
+    poses[0, :, 0] = 0.05 * torch.arange(n_frames, device=device)
+    intr = torch.tensor([320.0, 320.0, 320.0, 240.0], device=device).view(1, 1, 4).repeat(1, n_frames, 1)
+    return images, poses, disps, intr
+
+
+def run_train(args):
+    """BASELINE configs[3]: global batch 8 clips per optimiser step, split over the ranks (strong scaling: 1 GPU runs
+    8 clips with gradient accumulation, 8 GPUs one clip each), gradients averaged over NVLink by
+    dpvo_b200.multigpu.GradReducer (bucketed NCCL all-reduce launched from autograd hooks)."""
+    import numpy as np
+    import torch
+    import dpvo_b200
+    from dpvo_b200 import multigpu
+    from dpvo_b200.train import VONet, TrainStep
+    rank, world, local = multigpu.env_rank()
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    multigpu.init("nccl", dev)
+    ex = dpvo_b200.extensions()[3]
+    torch.manual_seed(1234); np.random.seed(1234 + rank)
+    net = VONet().to(dev).train()
+    red = multigpu.GradReducer(net.parameters())
+    step = TrainStep(net, steps_unrolled=18, total_steps=100000, reducer=red)
+    global_batch = 8
+    local_clips = max(1, global_batch // world)
+    pinned = [[t.cpu().pin_memory() for t in synthetic_clip(dev, 1234 + rank * 100 + c)] for c in range(local_clips)]
+
+    def one_step():
+        clips = [[t.to(dev, non_blocking=True) for t in c] for c in pinned]          # H2D of this step's inputs
+        loss, _ = step.step_clips(clips, structure_only=False)
+        return float(loss)                                                             # D2H of the loss
+
+    def barrier():
+        torch.cuda.synchronize(); multigpu.barrier(); torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 1)):
+        one_step()
+    if rank == 0:
+        sampler.wait_first()
+    barrier()
+    w0 = time.time()
+    l0 = ex.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        loss = one_step()
+    b.record()
+    barrier()
+    w1 = time.time()
+    launches = ex.launch_count() - l0
+    ms, = multigpu.max_over_ranks([a.elapsed_time(b) / args.steps], dev)
+    clocks = sampler.stop([(w0, w1)]) if rank == 0 else None
+    if rank == 0:
+        h2d = sum(t.numel() * t.element_size() for c in pinned for t in c)
+        clips_per_s = local_clips * world / (ms * 1e-3)
+        out = {"metric": TRAIN_METRIC, "value": clips_per_s, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+               "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (training runs without autocast, net.py:187)",
+               "data": "synthetic", "gpu_launches": int(launches), "clocks": clocks, "last_loss": loss,
+               "config": {"workload": "BASELINE configs[3]: training step, global batch 8 x 15 frames x 480x640, 80 patches/frame, STEPS=18", "global_batch": global_batch,
+                          "clips_per_rank": local_clips, "parallelism": "dp%d: one clip at a time per rank, NCCL all-reduce of %.2f MB fp32 gradients per step in %d buckets"
+                          % (world, red.bytes_per_step / 1e6, len(red.buckets)), "l2_policy": "inputs larger than L2 (15-frame fp32 feature pyramid 147 MB + activations)"},
+               "e2e": {"value": clips_per_s, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                       "note": "the timed step IS end to end: clips come from pinned host memory every step and the loss is read back"}}
+        print(json.dumps(out))
+    multigpu.finalize()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train = BASELINE configs[3] (training step, NCCL grad all-reduce)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
@@ -450,6 +535,10 @@ def main():
     ap.add_argument("--no-reference-cuda", action="store_true", help="skip the reference-CUDA-pipeline leg")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
     args = ap.parse_args()
+    if args.mode == "train":
+        args.steps = 3 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        return run_train(args)
     if args.steps is None:
         args.steps = 200 if args.impl == "ours" else 4
     if args.warmup is None:

@@ -18,6 +18,7 @@
 //       * all CTAs back-substitute the depth updates and retract the patches
 // Results are bit-reproducible run to run (the reference's are not: unordered atomics).
 #include "common.cuh"
+#include "ba_edge.cuh"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -48,131 +49,10 @@ struct BaArgs {
   long long* dbg; // optional phase timestamps of the solve kernel (cluster rank 0), NULL = off
 };
 
-// ---- Eigen-free SE3 helpers, same formulas as ba_cuda.cu:36-174 -------------------------
-__device__ __forceinline__ void actSO3(const float* q, const float* X, float* Y) {
-  float uv[3];
-  uv[0] = 2.0f * (q[1] * X[2] - q[2] * X[1]);
-  uv[1] = 2.0f * (q[2] * X[0] - q[0] * X[2]);
-  uv[2] = 2.0f * (q[0] * X[1] - q[1] * X[0]);
-  Y[0] = X[0] + q[3] * uv[0] + (q[1] * uv[2] - q[2] * uv[1]);
-  Y[1] = X[1] + q[3] * uv[1] + (q[2] * uv[0] - q[0] * uv[2]);
-  Y[2] = X[2] + q[3] * uv[2] + (q[0] * uv[1] - q[1] * uv[0]);
-}
-__device__ __forceinline__ void relSE3(const float* ti, const float* qi, const float* tj, const float* qj,
-                                       float* tij, float* qij) {
-  qij[0] = -qj[3] * qi[0] + qj[0] * qi[3] - qj[1] * qi[2] + qj[2] * qi[1];
-  qij[1] = -qj[3] * qi[1] + qj[1] * qi[3] - qj[2] * qi[0] + qj[0] * qi[2];
-  qij[2] = -qj[3] * qi[2] + qj[2] * qi[3] - qj[0] * qi[1] + qj[1] * qi[0];
-  qij[3] = qj[3] * qi[3] + qj[0] * qi[0] + qj[1] * qi[1] + qj[2] * qi[2];
-  actSO3(qij, ti, tij);
-  tij[0] = tj[0] - tij[0]; tij[1] = tj[1] - tij[1]; tij[2] = tj[2] - tij[2];
-}
-// Y = Adj(T)^T X for T = (t, q)   (ba_cuda.cu:57-72)
-__device__ __forceinline__ void adjSE3(const float* t, const float* q, const float* X, float* Y) {
-  const float qinv[4] = {-q[0], -q[1], -q[2], q[3]};
-  actSO3(qinv, &X[0], &Y[0]);
-  actSO3(qinv, &X[3], &Y[3]);
-  float u[3], v[3];
-  u[0] = t[2] * X[1] - t[1] * X[2];
-  u[1] = t[0] * X[2] - t[2] * X[0];
-  u[2] = t[1] * X[0] - t[0] * X[1];
-  actSO3(qinv, u, v);
-  Y[3] += v[0]; Y[4] += v[1]; Y[5] += v[2];
-}
-__device__ __forceinline__ void expSO3(const float* phi, float* q) {
-  const float theta_sq = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
-  const float theta_p4 = theta_sq * theta_sq;
-  const float theta = sqrtf(theta_sq);
-  float imag, real;
-  if (theta_sq < 1e-8f) {
-    imag = 0.5f - (1.0f / 48.0f) * theta_sq + (1.0f / 3840.0f) * theta_p4;
-    real = 1.0f - (1.0f / 8.0f) * theta_sq + (1.0f / 384.0f) * theta_p4;
-  } else {
-    imag = sinf(0.5f * theta) / theta;
-    real = cosf(0.5f * theta);
-  }
-  q[0] = imag * phi[0]; q[1] = imag * phi[1]; q[2] = imag * phi[2]; q[3] = real;
-}
-__device__ __forceinline__ void crossInplace(const float* a, float* b) {
-  const float x[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
-  b[0] = x[0]; b[1] = x[1]; b[2] = x[2];
-}
-__device__ __forceinline__ void expSE3(const float* xi, float* t, float* q) {
-  expSO3(xi + 3, q);
-  float tau[3] = {xi[0], xi[1], xi[2]};
-  const float phi[3] = {xi[3], xi[4], xi[5]};
-  const float theta_sq = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
-  const float theta = sqrtf(theta_sq);
-  t[0] = tau[0]; t[1] = tau[1]; t[2] = tau[2];
-  if (theta > 1e-4f) {
-    const float a = (1.0f - cosf(theta)) / theta_sq;
-    crossInplace(phi, tau);
-    t[0] += a * tau[0]; t[1] += a * tau[1]; t[2] += a * tau[2];
-    const float b = (theta - sinf(theta)) / (theta * theta_sq);
-    crossInplace(phi, tau);
-    t[0] += b * tau[0]; t[1] += b * tau[1]; t[2] += b * tau[2];
-  }
-}
-// pose <- Exp(xi) * pose   (ba_cuda.cu:156-174)
-__device__ __forceinline__ void retrSE3(const float* xi, const float* t, const float* q, float* t1, float* q1) {
-  float dt[3] = {0, 0, 0};
-  float dq[4] = {0, 0, 0, 1};
-  expSE3(xi, dt, dq);
-  q1[0] = dq[3] * q[0] + dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1];
-  q1[1] = dq[3] * q[1] + dq[1] * q[3] + dq[2] * q[0] - dq[0] * q[2];
-  q1[2] = dq[3] * q[2] + dq[2] * q[3] + dq[0] * q[1] - dq[1] * q[0];
-  q1[3] = dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2];
-  actSO3(dq, t, t1);
-  t1[0] += dt[0]; t1[1] += dt[1]; t1[2] += dt[2];
-}
-
-// ---- linearisation of one edge: both residual rows (ba_cuda.cu:265-333) ------------------
-struct EdgeLin {
-  float w[2], r[2], Jz[2];
-  float Ji[2][6];   // Adj^T Jj, as in the reference (enters with a minus sign)
-  float Jj[2][6];
-};
-
-__device__ __forceinline__ void linearize_edge(const BaArgs& a, int64_t e, float fx, float fy, float cx, float cy,
-                                               EdgeLin& L) {
-  const int64_t ix = a.ii[e], jx = a.jj[e], kx = a.kk[e];
-  const float* pi = a.poses + ix * 7;
-  const float* pj = a.poses + jx * 7;
-  const float ti[3] = {pi[0], pi[1], pi[2]}, qi[4] = {pi[3], pi[4], pi[5], pi[6]};
-  const float tj[3] = {pj[0], pj[1], pj[2]}, qj[4] = {pj[3], pj[4], pj[5], pj[6]};
-  const int P = a.P, c = P / 2;
-  const float* pk = a.patches + kx * 3 * P * P + c * P + c;
-  float Xi[4], Xj[4];
-  Xi[0] = (pk[0] - cx) / fx;
-  Xi[1] = (pk[P * P] - cy) / fy;
-  Xi[2] = 1.0f;
-  Xi[3] = pk[2 * P * P];
-  float tij[3], qij[4];
-  relSE3(ti, qi, tj, qj, tij, qij);
-  actSO3(qij, Xi, Xj);
-  Xj[3] = Xi[3];
-  Xj[0] += Xi[3] * tij[0]; Xj[1] += Xi[3] * tij[1]; Xj[2] += Xi[3] * tij[2];
-  const float X = Xj[0], Y = Xj[1], Z = Xj[2], W = Xj[3];
-  const float d = ((double)Z >= 0.2) ? 1.0f / Z : 0.0f;
-  const float d2 = d * d;
-  const float x1 = fx * (X / Z) + cx;
-  const float y1 = fy * (Y / Z) + cy;
-  const float rx = a.target[e * 2 + 0] - x1;
-  const float ry = a.target[e * 2 + 1] - y1;
-  const bool in_bounds = (sqrtf(rx * rx + ry * ry) < 128.0f) && ((double)Z > 0.2) && (x1 > -64.0f) &&
-                         (y1 > -64.0f) && (x1 < 2.0f * cx + 64.0f) && (y1 < 2.0f * cy + 64.0f);
-  const float mask = in_bounds ? 1.0f : 0.0f;
-  L.r[0] = rx; L.r[1] = ry;
-  L.w[0] = mask * a.weight[e * 2 + 0];
-  L.w[1] = mask * a.weight[e * 2 + 1];
-  L.Jz[0] = fx * (tij[0] * d - tij[2] * (X * d2));
-  L.Jz[1] = fy * (tij[1] * d - tij[2] * (Y * d2));
-  L.Jj[0][0] = fx * W * d; L.Jj[0][1] = 0.0f; L.Jj[0][2] = fx * -X * W * d2;
-  L.Jj[0][3] = fx * -X * Y * d2; L.Jj[0][4] = fx * (1.0f + X * X * d2); L.Jj[0][5] = fx * -Y * d;
-  L.Jj[1][0] = 0.0f; L.Jj[1][1] = fy * W * d; L.Jj[1][2] = fy * -Y * W * d2;
-  L.Jj[1][3] = fy * (-1.0f - Y * Y * d2); L.Jj[1][4] = fy * (X * Y * d2); L.Jj[1][5] = fy * X * d;
-  adjSE3(tij, qij, L.Jj[0], L.Ji[0]);
-  adjSE3(tij, qij, L.Jj[1], L.Ji[1]);
+// per-edge linearisation (own SE3 operators of lie.cuh, see ba_edge.cuh)
+__device__ __forceinline__ void linearize_edge(const BaArgs& a, int64_t e, float fx, float fy, float cx, float cy, EdgeLin& L) {
+  const EdgeCam K = {fx, fy, cx, cy};
+  linearize_edge_at(a.poses, a.patches, a.P, a.target, a.weight, e, a.ii[e], a.jj[e], a.kk[e], K, L);
 }
 
 // ==========================================================================================
@@ -701,14 +581,7 @@ ba_solve_kernel(const BaArgs a) {
   cluster.sync();
   BA_STAMP(10);
   if (N > 0 && rank == 0 && tid < N) {
-    float* pp = a.poses + (int64_t)(a.t0 + tid) * 7;
-    const float t[3] = {pp[0], pp[1], pp[2]}, q[4] = {pp[3], pp[4], pp[5], pp[6]};
-    float xi[6];
-    for (int k = 0; k < 6; ++k) xi[k] = sm.dx[6 * tid + k];
-    float t1[3], q1[4];
-    retrSE3(xi, t, q, t1, q1);
-    pp[0] = t1[0]; pp[1] = t1[1]; pp[2] = t1[2];
-    pp[3] = q1[0]; pp[4] = q1[1]; pp[5] = q1[2]; pp[6] = q1[3];
+    retract_pose(a.poses + (int64_t)(a.t0 + tid) * 7, sm.dx + 6 * tid);
   }
 }
 
@@ -722,30 +595,16 @@ __global__ void reproject_kernel(const float* __restrict__ poses, const float* _
                                  float* __restrict__ coords, int64_t E, int P) {
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < E; n += (int64_t)gridDim.x * blockDim.x) {
     const int64_t ix = ii[n], jx = jj[n], kx = kk[n];
-    const float* pi = poses + ix * 7;
-    const float* pj = poses + jx * 7;
-    float ti[3] = {pi[0], pi[1], pi[2]}, qi[4] = {pi[3], pi[4], pi[5], pi[6]};
-    float tj[3] = {pj[0], pj[1], pj[2]}, qj[4] = {pj[3], pj[4], pj[5], pj[6]};
     const float* Ki = CLAMP ? intrinsics + ix * 4 : intrinsics;
     const float* Kj = CLAMP ? intrinsics + jx * 4 : intrinsics;
-    if (CLAMP) {
-      // lietorch normalises quaternions when it loads a group element (so3.h:35-37)
-      const float ni = rsqrtf(qi[0] * qi[0] + qi[1] * qi[1] + qi[2] * qi[2] + qi[3] * qi[3]);
-      const float nj = rsqrtf(qj[0] * qj[0] + qj[1] * qj[1] + qj[2] * qj[2] + qj[3] * qj[3]);
-      for (int k = 0; k < 4; ++k) { qi[k] *= ni; qj[k] *= nj; }
-    }
-    float tij[3], qij[4];
-    relSE3(ti, qi, tj, qj, tij, qij);
+    // the lietorch path (pops.transform) loads group elements normalised (so3.h:35-37); cuda_ba.reproject does not
+    const lie::SE3<float> G = edge_relative_pose(poses, ix, jx, CLAMP);
     const float* pk = patches + kx * 3 * P * P;
     float* out = coords + n * 2 * P * P;
     for (int i = 0; i < P * P; ++i) {
-      float Xi[4], Xj[3];
-      Xi[0] = (pk[i] - Ki[2]) / Ki[0];
-      Xi[1] = (pk[P * P + i] - Ki[3]) / Ki[1];
-      Xi[2] = 1.0f;
-      Xi[3] = pk[2 * P * P + i];
-      actSO3(qij, Xi, Xj);
-      Xj[0] += Xi[3] * tij[0]; Xj[1] += Xi[3] * tij[1]; Xj[2] += Xi[3] * tij[2];
+      const lie::V3<float> p = lie::v3<float>((pk[i] - Ki[2]) / Ki[0], (pk[P * P + i] - Ki[3]) / Ki[1], 1.0f);
+      const lie::V3<float> Pj = lie::q_rot(G.q, p) + pk[2 * P * P + i] * G.t;
+      const float Xj[3] = {Pj.x, Pj.y, Pj.z};
       if (CLAMP) {
         const float d = 1.0f / fmaxf(Xj[2], 0.1f);
         out[i] = Kj[0] * (d * Xj[0]) + Kj[2];

@@ -121,13 +121,12 @@ std::vector<Tensor> patchify_backward(Tensor net, Tensor coords, Tensor gradient
 }
 
 // -------------------------------------------------------------------------------- cuda_ba
+std::vector<Tensor> group_edges(Tensor key_a, c10::optional<Tensor> key_b, c10::optional<Tensor> sec);
 std::vector<Tensor> ba_forward(Tensor poses, Tensor patches, Tensor intrinsics, Tensor target, Tensor weight,
                                Tensor lmbda, Tensor ii, Tensor jj, Tensor kk, int PPF, int t0, int t1,
                                int iterations, bool eff_impl) {
   need_cuda(poses, "poses"); need_cuda(patches, "patches");
   c10::cuda::CUDAGuard guard(poses.device());
-  TORCH_CHECK(!eff_impl, "cuda_ba.forward: eff_impl=True (block-sparse global BA, loop closure) is not built in dpvo_b200");
-  (void)PPF;
   TORCH_CHECK(poses.is_contiguous() && patches.is_contiguous(), "cuda_ba.forward updates poses/patches in place: they must be contiguous");
   TORCH_CHECK(poses.scalar_type() == at::kFloat && patches.scalar_type() == at::kFloat, "cuda_ba.forward: poses/patches must be float32");
   const int P = patches.size(-1);
@@ -139,6 +138,34 @@ std::vector<Tensor> ba_forward(Tensor poses, Tensor patches, Tensor intrinsics, 
   const int64_t E = ii.numel();
   TORCH_CHECK(jj.numel() == E && kk.numel() == E && target.size(0) == E && weight.size(0) == E, "cuda_ba.forward: edge arrays disagree in length");
   const int64_t n_poses = poses.numel() / 7, n_patches = patches.numel() / (3 * P * P);
+  const int N = t1 - t0;
+  if (N > 0 && E > 0 && iterations > 0 && (eff_impl || N > 32)) {
+    // wide windows / global BA (dpvo.py:312-326): block-sparse Schur complement per source frame (ba_wide.cu), dense
+    // Cholesky of the 6N x 6N system by the library -- ba_cuda.cu:547-549 does the same -- then back-substitution
+    TORCH_CHECK(PPF > 0, "cuda_ba.forward: patches per frame must be positive");
+    std::vector<Tensor> g = group_edges(ii, jj, c10::nullopt);
+    Tensor S = torch::empty({6 * N, 6 * N}, poses.options()), y = torch::empty({6 * N}, poses.options());
+    Tensor status = torch::zeros({1}, poses.options().dtype(at::kInt));
+    for (int it = 0; it < iterations; ++it) {
+      check(dpvo_ba_wide_system(poses.data_ptr<float>(), patches.data_ptr<float>(), intrinsics.data_ptr<float>(), target.data_ptr<float>(),
+                                weight.data_ptr<float>(), lmbda.data_ptr<float>(), ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(),
+                                kk.data_ptr<int64_t>(), E, P, PPF, t0, t1, g[0].data_ptr<int>(), g[2].data_ptr<int>(), g[3].data_ptr<int64_t>(),
+                                g[4].data_ptr<int64_t>(), g[5].data_ptr<int>(), S.data_ptr<float>(), y.data_ptr<float>(), status.data_ptr<int>(),
+                                stream()),
+            "cuda_ba.forward (wide)");
+      Tensor L = std::get<0>(at::linalg_cholesky_ex(S));
+      Tensor dX = at::cholesky_solve(y.view({6 * N, 1}), L).contiguous();
+      check(dpvo_ba_wide_update(poses.data_ptr<float>(), patches.data_ptr<float>(), intrinsics.data_ptr<float>(), target.data_ptr<float>(),
+                                weight.data_ptr<float>(), lmbda.data_ptr<float>(), ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(),
+                                kk.data_ptr<int64_t>(), E, P, PPF, t0, t1, g[0].data_ptr<int>(), g[2].data_ptr<int>(), g[3].data_ptr<int64_t>(),
+                                g[4].data_ptr<int64_t>(), g[5].data_ptr<int>(), dX.data_ptr<float>(), status.data_ptr<int>(), stream()),
+            "cuda_ba.forward (wide)");
+    }
+    const int st = status.item<int>();
+    TORCH_CHECK(st == 0, st == 1 ? "cuda_ba.forward (wide): a frame is observed from more frames than the on-chip product holds"
+                                 : "cuda_ba.forward (wide): patch ids must be frame * PPF + slot (as dpvo/fastba/block_e.cu assumes)");
+    return {};
+  }
   const int64_t wsb = dpvo_ba_workspace_bytes(E, t1 - t0);
   Tensor ws = byte_ws(wsb, poses);
   check(dpvo_ba_forward(poses.data_ptr<float>(), patches.data_ptr<float>(), intrinsics.data_ptr<float>(),
@@ -182,9 +209,32 @@ Tensor ba_reproject(Tensor poses, Tensor patches, Tensor intrinsics, Tensor ii, 
   return reproject_impl(poses, patches, intrinsics, ii, jj, kk, 0);
 }
 
-std::vector<Tensor> ba_solve_system(Tensor, Tensor, Tensor, Tensor, Tensor, float, float, int) {
-  TORCH_CHECK(false, "cuda_ba.solve_system (CPU sparse pose-graph solve, loop closure only) is not built in dpvo_b200");
-  return {};
+// cuda_ba.solve_system (ba.cpp:120-180): pose-graph Gauss-Newton step of the loop-closure back end.  The normal
+// equations are assembled on the device in fp64 (the reference: Eigen sparse, fp64, on the CPU); the leading
+// 7*freen block is solved by a dense Cholesky and the remaining poses get a zero step (ba.cpp:101-118).
+std::vector<Tensor> ba_solve_system(Tensor J_Ginv_i, Tensor J_Ginv_j, Tensor ii, Tensor jj, Tensor res, float ep, float lm, int freen) {
+  need_cuda(res, "res");
+  c10::cuda::CUDAGuard guard(res.device());
+  J_Ginv_i = f32c(J_Ginv_i.to(res.device())); J_Ginv_j = f32c(J_Ginv_j.to(res.device()));
+  ii = i64c(ii.to(res.device())); jj = i64c(jj.to(res.device()));
+  Tensor r32 = f32c(res).view({-1, 7});
+  const int64_t r = r32.size(0);
+  TORCH_CHECK(J_Ginv_i.numel() == r * 49 && J_Ginv_j.numel() == r * 49 && ii.numel() == r && jj.numel() == r, "cuda_ba.solve_system: shape mismatch");
+  TORCH_CHECK(r > 0, "cuda_ba.solve_system: no residuals");
+  TORCH_CHECK(!(ii == jj).any().item<bool>(), "cuda_ba.solve_system: an edge connects a pose to itself");      // ba.cpp:152 exits
+  const int64_t n = std::max(ii.max().item<int64_t>(), jj.max().item<int64_t>()) + 1;
+  auto od = res.options().dtype(at::kDouble);
+  Tensor A = torch::empty({n * 7, n * 7}, od), b = torch::empty({n * 7}, od);
+  check(dpvo_posegraph_system(J_Ginv_i.data_ptr<float>(), J_Ginv_j.data_ptr<float>(), ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(),
+                              r32.data_ptr<float>(), r, n, (double)ep, (double)lm, A.data_ptr<double>(), b.data_ptr<double>(), stream()),
+        "cuda_ba.solve_system");
+  const int64_t f = freen < 0 ? n * 7 : std::min<int64_t>((int64_t)freen * 7, n * 7);
+  Tensor delta = torch::zeros({n * 7}, od);
+  if (f > 0) {
+    Tensor L = std::get<0>(at::linalg_cholesky_ex(A.slice(0, 0, f).slice(1, 0, f).contiguous()));
+    delta.slice(0, 0, f).copy_(at::cholesky_solve(b.slice(0, 0, f).view({f, 1}), L).view({f}));
+  }
+  return {delta.to(at::kFloat).view({n, 7})};
 }
 
 // ------------------------------------------------------------------------ lietorch_backends
@@ -572,7 +622,7 @@ PYBIND11_MODULE(cuda_ba, m) {
   m.def("forward", &ba_forward, "BA forward operator");
   m.def("neighbors", &ba_neighbors, "temporal neighbor indices");
   m.def("reproject", &ba_reproject, "fused reprojection");
-  m.def("solve_system", &ba_solve_system, "pose-graph solve (not built)");
+  m.def("solve_system", &ba_solve_system, "pose-graph normal equations + solve (loop closure back end)");
 }
 
 PYBIND11_MODULE(lietorch_backends, m) {

@@ -50,7 +50,10 @@ class GatedResidual(nn.Module):
 
 
 class SoftAgg(nn.Module):
-    """Parameters only; the reduction runs in dpvo_softagg_reduce."""
+    """blocks.py:31-48.  Inference: parameters only, the reduction runs in dpvo_softagg_reduce.  Training:
+    `forward(x, group_of, n_groups)` is the differentiable fp32 form -- a per-group softmax of g(x) weighting f(x),
+    summed per group, mapped by h and handed back to every member; group ids come from the device grouping kernel
+    (no torch.unique), the per-group max / sums are index reductions."""
 
     def __init__(self, dim=512, expand=True):
         super().__init__()
@@ -58,6 +61,17 @@ class SoftAgg(nn.Module):
         self.f = nn.Linear(dim, dim)
         self.g = nn.Linear(dim, dim)
         self.h = nn.Linear(dim, dim)
+
+    def forward(self, x, group_of, n_groups):
+        logits = self.g(x)
+        idx = group_of.view(1, -1, 1).expand_as(logits)
+        top = torch.full((x.shape[0], n_groups, x.shape[2]), float("-inf"), dtype=x.dtype, device=x.device)
+        top = top.scatter_reduce(1, idx, logits.detach(), reduce="amax", include_self=True)
+        e = torch.exp(logits - top[:, group_of])               # the shift cancels in the ratio: no gradient through it
+        den = torch.zeros_like(top).index_add_(1, group_of, e)
+        y = torch.zeros_like(top).index_add_(1, group_of, self.f(x) * (e / den[:, group_of]))
+        y = self.h(y)
+        return y[:, group_of] if self.expand else y
 
 
 class EdgeGroups:
@@ -142,9 +156,32 @@ class Update(nn.Module):
         self._packed = P
         return P
 
+    # ------------------------------------------------------------------------------- training forward
+    def forward_train(self, net, inp, corr, flow, ii, jj, kk):
+        """Differentiable fp32 form of net.py:74-92 (training runs without autocast, net.py:187): torch dense layers
+        and LayerNorm with autograd, the temporal neighbours from our cuda_ba.neighbors kernel, both aggregations
+        on groupings built by one launch of the device radix sort.  Same parameters, same arithmetic order as the
+        reference module, so losses and gradients are comparable at fp32 round-off (tests/test_train_gpu.py)."""
+        net = self.norm(net + inp + self.corr(corr))
+        ix, jx = extensions()[1].neighbors(kk, jj)
+        for idx, mlp in ((ix, self.c1), (jx, self.c2)):
+            live = (idx >= 0).to(net.dtype).view(1, -1, 1)
+            net = net + mlp(live * net[:, idx])
+        gk, gp = EdgeGroups.pair((kk, None, jj), (ii, jj, None))
+        net = net + self.agg_kk(net, gk.group_of.long(), gk.max_groups)
+        net = net + self.agg_ij(net, gp.group_of.long(), gp.max_groups)
+        net = self.gru(net)
+        return net, (self.d(net), self.w(net), None)
+
     # ------------------------------------------------------------------------------- forward
-    @torch.no_grad()
     def forward(self, net, inp, corr, flow, ii, jj, kk, groups_kk=None, groups_ij=None, inp_index=None, coords=None):
+        """training mode with autograd enabled -> the differentiable fp32 path; otherwise the fused inference kernels"""
+        if self.training and torch.is_grad_enabled():
+            return self.forward_train(net, inp, corr, flow, ii, jj, kk)
+        with torch.no_grad():
+            return self.forward_infer(net, inp, corr, flow, ii, jj, kk, groups_kk, groups_ij, inp_index, coords)
+
+    def forward_infer(self, net, inp, corr, flow, ii, jj, kk, groups_kk=None, groups_ij=None, inp_index=None, coords=None):
         """net [1,E,384] (fp16 or fp32), inp [1,E,384], corr [1,E,882 or 896], ii/jj/kk int64 [E].
         Returns (net fp32, (delta [1,E,2], weight [1,E,2], None)) like net.py:92.
         Optional fusions for the inference loop: `inp_index` -- `inp` is the whole context table and row

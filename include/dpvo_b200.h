@@ -233,6 +233,38 @@ int dpvo_ba_forward_grouped(float* poses, float* patches, const float* intrinsic
                             void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * Wide windows / cuda_ba.forward(..., eff_impl=True) -- replaces dpvo/fastba/block_e.cu:38-299 (EfficentE) and
+ * the eff_impl branch of ba_cuda.cu:495-563.  For any number of free poses N = t1 - t0: one call assembles
+ *     S = B - E diag(Q) E^T + I o (1e-4 S + 1)   fp32 [6N, 6N]  and   y = v - E diag(Q) u   fp32 [6N]
+ * (the block-sparse pose/depth coupling E is never materialised: one CTA per source frame forms its dense
+ * product in shared memory); the caller solves S dX = y (dense Cholesky -- a library call, as in the reference,
+ * ba_cuda.cu:547-549) and hands dX to dpvo_ba_wide_update, which back-substitutes the depths, retracts patches
+ * and poses in place.  Requires the DPVO patch numbering kk = frame * PPF + slot (as block_e.cu does) and the
+ * (ii, jj) pair grouping of dpvo_group_edges(ii, jj, NULL).  `status` is a zero-initialised device int:
+ * after the stream has drained, 1 = a frame is observed from more frames than fit on chip, 2 = a patch id lies
+ * outside its frame's slot range; the results are then invalid.
+ */
+int dpvo_ba_wide_system(float* poses, float* patches, const float* intrinsics, const float* target, const float* weight,
+                        const float* lmbda, const int64_t* ii, const int64_t* jj, const int64_t* kk, int64_t E, int P, int PPF,
+                        int t0, int t1, const int32_t* p_order, const int32_t* p_start, const int64_t* p_key_i,
+                        const int64_t* p_key_j, const int32_t* p_n, float* S, float* y, int* status, void* stream);
+int dpvo_ba_wide_update(float* poses, float* patches, const float* intrinsics, const float* target, const float* weight,
+                        const float* lmbda, const int64_t* ii, const int64_t* jj, const int64_t* kk, int64_t E, int P, int PPF,
+                        int t0, int t1, const int32_t* p_order, const int32_t* p_start, const int64_t* p_key_i,
+                        const int64_t* p_key_j, const int32_t* p_n, const float* dX, int* status, void* stream);
+
+/*
+ * cuda_ba.solve_system -- ba.cpp:120-180 (pose-graph optimisation of the loop-closure back end,
+ * loop_closure/optim_utils.py:229): normal equations of r relative-pose residuals with 7x7 Jacobian blocks,
+ *     A = J^T J  (fp64 [7n, 7n]),  b = -J^T res  (fp64 [7n]),  A.diag += lm * A.diag + ep.
+ * The reference builds them in an Eigen sparse matrix on the CPU; here one kernel scatters the four 7x7 block
+ * products of every residual.  The caller solves the leading 7*freen x 7*freen system (dense Cholesky).
+ * J_i, J_j fp32 [r, 7, 7], res fp32 [r, 7], ii, jj int64 [r] (ii != jj), A and b zeroed by the call.
+ */
+int dpvo_posegraph_system(const float* J_i, const float* J_j, const int64_t* ii, const int64_t* jj, const float* res,
+                          int64_t r, int64_t n, double ep, double lm, double* A, double* b, void* stream);
+
+/*
  * cuda_ba.reproject -- ba_cuda.cu:585-617 (kernel :379-429): coords fp32 [E, 2, P, P].
  * clamp_depth = 0 reproduces the kernel (divide by raw Z, :422-423, intrinsics row 0);
  * clamp_depth = 1 reproduces pops.transform (projective_ops.py:53-68: Z clamped to >= 0.1 in

@@ -323,3 +323,24 @@ def python_ba(poses, patches, intrinsics, targets, weights, lmbda, ii, jj, kk, b
         full = _scatter_sum(dX, fixedp + torch.arange(n), poses.shape[1])
         poses = lie.se3_mul(lie.se3_exp(full), poses)
     return poses, patches
+
+
+def posegraph_solve(J_i, J_j, ii, jj, res, ep, lm, freen):
+    """cuda_ba.solve_system restated densely (dpvo/fastba/ba.cpp:99-180): stack the r x 7 residual rows with their
+    two 7x7 Jacobian blocks into J [7r, 7n], A = J^T J, b = -J^T res, A.diag += lm * A.diag + ep, solve the leading
+    7*freen block (all of it when freen < 0), zero step for the rest.  fp64 like the reference's Eigen path.
+    Parity unpinned: the reference function needs Eigen (absent from the image) and has no test or fixture."""
+    r = res.shape[0]
+    n = int(max(ii.max(), jj.max())) + 1
+    J = torch.zeros(r * 7, n * 7, dtype=torch.float64)
+    for x in range(r):
+        J[x * 7:(x + 1) * 7, int(ii[x]) * 7:(int(ii[x]) + 1) * 7] += J_i[x].double()
+        J[x * 7:(x + 1) * 7, int(jj[x]) * 7:(int(jj[x]) + 1) * 7] += J_j[x].double()
+    A = J.t() @ J
+    b = -(J.t() @ res.double().reshape(-1))
+    d = torch.diagonal(A)
+    d += d * lm + ep
+    f = n * 7 if freen < 0 else min(freen * 7, n * 7)
+    delta = torch.zeros(n * 7, dtype=torch.float64)
+    delta[:f] = torch.linalg.solve(A[:f, :f], b[:f])
+    return delta.view(n, 7)

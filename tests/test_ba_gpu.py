@@ -158,11 +158,68 @@ def test_reproject_both_modes(ext):
     assert (out2[0].cpu().double() - ref2[0].permute(0, 3, 1, 2)).abs().max().item() < 2e-3
 
 
-def test_ba_rejects_what_it_does_not_build(ext):
-    st, target, weight = _problem("fast", 12, 26)
-    poses = st.poses.clone().to(DEV)[None]
-    patches = st.patches.clone().to(DEV)[None]
-    args = (poses, patches, st.intrinsics.to(DEV)[None], target.to(DEV)[None], weight.to(DEV)[None],
-            torch.tensor([1e-4], device=DEV), st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV), st.cfg["M"])
+def _wide_graph(n_frames=40, M=24, seed=60):
+    """a long window with a few loop-closure style long-range edges: the shape global BA sees (dpvo.py:312-326)"""
+    st = synthetic.make_state(dict(M=M, lifetime=8, removal=40, opt_window=39, ht=480, wd=640, intrinsics=(320.0, 320.0, 320.0, 240.0)),
+                              n_frames, device="cpu", features=False, seed=seed, buffer=n_frames + 2, mem=n_frames + 2)
+    # long-range edges: patches of frames 0..2 observed again in the last three frames
+    g = torch.Generator().manual_seed(seed)
+    kk_l = torch.arange(0, 3 * M).repeat_interleave(3)
+    jj_l = torch.arange(n_frames - 3, n_frames).repeat(3 * M)
+    st.ii = torch.cat([st.ii, kk_l // M]); st.jj = torch.cat([st.jj, jj_l]); st.kk = torch.cat([st.kk, kk_l])
+    coords = OB.fastba_reproject(st.poses.double(), st.patches.double(), st.intrinsics.double(), st.ii, st.jj, st.kk)
+    target = (coords[:, :, 1, 1] + torch.randn(st.E, 2, generator=g).double()).float()
+    weight = torch.rand(st.E, 2, generator=g)
+    return st, target, weight
+
+
+@pytest.mark.parametrize("eff_impl,t0", [(True, 1), (False, 1), (True, 20)])
+def test_ba_wide_window_and_eff_impl_match_oracle_and_reference_kernel(ext, ref_ext, eff_impl, t0):
+    """cuda_ba.forward with eff_impl=True (block_e.cu path of the reference) and / or more than 32 free poses: our
+    per-frame Schur product (ba_wide.cu) vs the dense fp64 oracle and vs the reference's own kernel, 1e-4 relative"""
+    st, target, weight = _wide_graph()
+    lm = torch.tensor([1e-4])
+    rp, rq = OB.fastba_forward(st.poses.double(), st.patches.double(), st.intrinsics.double(), target.double(), weight.double(),
+                               lm.double(), st.ii, st.jj, st.kk, t0, st.n, 2)
+    outs = []
+    for mod in ([ext[1]] + ([ref_ext[1]] if ref_ext is not None else [])):
+        poses, patches = st.poses.clone().to(DEV)[None], st.patches.clone().to(DEV)[None]
+        mod.forward(poses, patches, st.intrinsics.to(DEV)[None], target.to(DEV)[None], weight.to(DEV)[None], lm.to(DEV),
+                    st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV), st.cfg["M"], t0, st.n, 2, eff_impl)
+        outs.append((poses[0, :st.n].cpu().double(), patches[0].cpu().double()))
+    live = st.kk.unique()
+    assert st.n - t0 > 32 or eff_impl
+    for p, q in outs:
+        assert torch.isfinite(p).all() and torch.isfinite(q[live]).all()
+        assert _rel(p, rp[:st.n]) < 1e-4 and _rel(q[live, 2], rq[live, 2]) < 1e-4
+    assert (outs[0][0] - st.poses[:st.n].double()).abs().max().item() > 1e-4      # the step moved the poses
+    if t0 > 1:
+        assert torch.equal(outs[0][0][:t0].float(), st.poses[:t0])                 # poses before t0 stay fixed
+
+
+def test_ba_wide_rejects_patch_ids_outside_their_frame(ext):
+    st, target, weight = _wide_graph(n_frames=36, M=8)
+    kk_bad = st.kk.clone()
+    kk_bad[5] = kk_bad[5] + 8                      # patch no longer belongs to frame ii[5]
+    poses, patches = st.poses.clone().to(DEV)[None], st.patches.clone().to(DEV)[None]
     with pytest.raises(RuntimeError):
-        ext[1].forward(*args, 1, st.n, 2, True)           # eff_impl (global BA) not built
+        ext[1].forward(poses, patches, st.intrinsics.to(DEV)[None], target.to(DEV)[None], weight.to(DEV)[None], torch.tensor([1e-4], device=DEV),
+                       st.ii.to(DEV), st.jj.to(DEV), kk_bad.to(DEV), 8, 1, st.n, 1, True)
+
+
+def test_solve_system_matches_dense_restatement(ext):
+    """cuda_ba.solve_system (ba.cpp:120-180): A = J^T J with 7x7 blocks, damping, solve of the leading freen poses"""
+    g = torch.Generator().manual_seed(70)
+    n, r = 12, 40
+    ii = torch.randint(0, n, (r,), generator=g)
+    jj = (ii + 1 + torch.randint(0, n - 1, (r,), generator=g)) % n
+    Ji = torch.randn(r, 7, 7, generator=g) * 0.5 + torch.eye(7)
+    Jj = torch.randn(r, 7, 7, generator=g) * 0.5 - torch.eye(7)
+    res = torch.randn(r, 7, generator=g)
+    for freen in (-1, 9):
+        out, = ext[1].solve_system(Ji.to(DEV), Jj.to(DEV), ii.to(DEV), jj.to(DEV), res.to(DEV), 1e-3, 1e-4, freen)
+        ref = OB.posegraph_solve(Ji.double(), Jj.double(), ii, jj, res.double(), 1e-3, 1e-4, freen)
+        assert out.shape == (n, 7) and out.dtype == torch.float32
+        assert (out.cpu().double() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+        if freen > 0:
+            assert torch.equal(out[freen:].cpu(), torch.zeros(n - freen, 7))

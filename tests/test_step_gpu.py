@@ -33,9 +33,11 @@ def composed_oracle_step(st, mod32, net, kk_ring, jj_ring, iters=2):
     corr = torch.stack([c0, c1], -1).view(1, st.E, -1)
     net, (delta, weight, _) = mod32(net, st.imap[:, kk_ring].float(), corr, None, st.ii, st.jj, st.kk)
     target = coords[..., 1, 1] + delta
-    lm = torch.tensor([1e-4], dtype=torch.float64, device=poses.device)
-    p, q = OB.fastba_forward(st.poses.double(), st.patches.double(), st.intrinsics.double(), target[0].double(), weight[0].double(),
-                             lm, st.ii, st.jj, st.kk, st.t0, st.n, iters)
+    # the BA restatement runs on the host (fp64)
+    lm = torch.tensor([1e-4], dtype=torch.float64)
+    p, q = OB.fastba_forward(st.poses.cpu().double(), st.patches.cpu().double(), st.intrinsics.cpu().double(), target[0].cpu().double(),
+                             weight[0].cpu().double(), lm, st.ii.cpu(), st.jj.cpu(), st.kk.cpu(), st.t0, st.n, iters)
+    p, q = p.to(poses.device), q.to(poses.device)
     return dict(poses=p[:st.n], depth=q[:, 2, 1, 1], target=target, weight=weight, net=net, corr=corr, coords=coords)
 
 
@@ -89,8 +91,9 @@ def test_full_update_step_vs_oracle_and_reference_pipeline(ext, ref_ext, config,
     lm = torch.tensor([1e-4], device=DEV)
     p_ref, q_ref = poses0.clone()[None], patches0.clone()[None]
     ref_ext[1].forward(p_ref, q_ref, st.intrinsics[None], tgt, wgt, lm, st.ii, st.jj, st.kk, st.cfg["M"], st.t0, st.n, 2, False)
-    p_o, q_o = OB.fastba_forward(poses0.double(), patches0.double(), st.intrinsics.double(), tgt[0].double(), wgt[0].double(),
-                                 lm.double(), st.ii, st.jj, st.kk, st.t0, st.n, 2)
+    p_o, q_o = OB.fastba_forward(poses0.cpu().double(), patches0.cpu().double(), st.intrinsics.cpu().double(), tgt[0].cpu().double(),
+                                 wgt[0].cpu().double(), lm.cpu().double(), st.ii.cpu(), st.jj.cpu(), st.kk.cpu(), st.t0, st.n, 2)
+    p_o, q_o = p_o.to(DEV), q_o.to(DEV)
     assert _rel(ours["poses"], p_ref[0, :st.n]) < 1e-4 and _rel(ours["depth"][live], q_ref[0, :, 2, 1, 1][live]) < 1e-4
     assert _rel(ours["poses"], p_o[:st.n]) < 1e-4 and _rel(ours["depth"][live], q_o[:, 2, 1, 1][live]) < 1e-4
 

@@ -1,0 +1,151 @@
+"""Training path on the device (BASELINE configs[3]): the differentiable update operator, the differentiable
+BA and the whole unrolled training forward + loss + backward, against the oracle and against the REFERENCE's
+own dpvo/net.py:VONet.forward (unmodified Python from oracle/_ref/dpvo_ref_py.zip, executing on our native
+modules) with the random draws aligned."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ba as OB, update as OU, refimport
+from dpvo_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_update_forward_train_matches_oracle_module_and_its_gradients(ext):
+    from dpvo_b200.net import Update
+    st = synthetic.make_state("fast", 12, device="cpu", features=False)
+    E = st.E
+    torch.manual_seed(4)
+    ref = OU.Update(3).to(DEV).train()
+    ours = Update(3).to(DEV).train()
+    ours.load_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(5)
+    net = (torch.randn(1, E, 384, generator=g) * 0.5).to(DEV).requires_grad_(True)
+    inp = (torch.randn(1, E, 384, generator=g) * 0.25).to(DEV)
+    corr = (torch.randn(1, E, 882, generator=g) * 2).to(DEV).requires_grad_(True)
+    ii, jj, kk = st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV)
+    cn = torch.randn(1, E, 384, generator=g).to(DEV)
+    cd = torch.randn(1, E, 2, generator=g).to(DEV)
+    outs = []
+    for mod in (ref, ours):
+        mod.zero_grad()
+        n, (d, w, _) = mod(net, inp, corr, None, ii, jj, kk)
+        loss = (n * cn).sum() + (d * cd).sum() * 50 + (w * cd).sum() * 50
+        gn, gc = torch.autograd.grad(loss, (net, corr), retain_graph=True)
+        loss.backward()
+        outs.append((n.detach(), d.detach(), w.detach(), gn, gc, {k: p.grad.clone() for k, p in mod.named_parameters()}))
+    (n0, d0, w0, gn0, gc0, p0), (n1, d1, w1, gn1, gc1, p1) = outs
+    assert ours.training and n1.requires_grad is False
+    for a, b, nm in ((n1, n0, "net"), (d1, d0, "delta"), (w1, w0, "weight"), (gn1, gn0, "dnet"), (gc1, gc0, "dcorr")):
+        assert (a - b).abs().max().item() <= 2e-4 * max(1.0, b.abs().max().item()), nm
+    # parameters whose exact gradient is zero (the per-group softmax is invariant to the bias of g) carry only round-off:
+    # errors are judged against the largest gradient of the module as well as against the tensor's own size
+    gmax = max(v.abs().max().item() for v in p0.values())
+    for k in p0:
+        assert (p1[k] - p0[k]).abs().max().item() <= 1e-3 * max(1e-4 * gmax, p0[k].abs().max().item()), k
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 2e-3)])
+def test_differentiable_ba_on_device_matches_python_ba_oracle(ext, dtype, tol):
+    """dpvo_b200.ba.BA on the device kernels vs oracle/ba.py:python_ba (bit-exact vs the reference's dpvo/ba.py on CPU)"""
+    from dpvo_b200.ba import BA
+    from dpvo_b200.lietorch import SE3
+    st = synthetic.make_state("fast", 12, device="cpu", features=False, seed=31, noise=0.02, buffer=16)
+    g = torch.Generator().manual_seed(32)
+    n = st.n
+    poses, patches, intr = st.poses.double()[None, :n], st.patches.double()[None, :n * 48], st.intrinsics.double()[None, :n]
+    coords = OB.transform(poses, patches, intr, st.ii, st.jj, st.kk)
+    target = coords[..., 1, 1, :] + torch.randn(1, st.E, 2, generator=g).double()
+    weight = torch.rand(1, st.E, 2, generator=g).double()
+    bounds = [-64, -64, 188 + 64, 120 + 64]
+    P, Q = poses, patches
+    for _ in range(2):
+        P, Q = OB.python_ba(P, Q, intr, target, weight, 1e-4, st.ii, st.jj, st.kk, bounds, ep=10.0, fixedp=1)
+    G, q = SE3(poses.to(DEV, dtype)), patches.to(DEV, dtype)
+    for _ in range(2):
+        G, q = BA(G, q, intr.to(DEV, dtype), target.to(DEV, dtype), weight.to(DEV, dtype), 1e-4, st.ii.to(DEV), st.jj.to(DEV), st.kk.to(DEV),
+                  bounds, ep=10.0, fixedp=1)
+    assert (G.data.cpu().double() - P).abs().max().item() <= tol * P.abs().max().item()
+    assert (q.cpu().double() - Q).abs().max().item() <= tol * Q.abs().max().item()
+
+
+def _clip(n_frames=10, ht=128, wd=160, seed=3):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    images = (torch.rand(1, n_frames, 3, ht, wd, generator=g, device=DEV) * 255).floor()
+    k = torch.ones(3, 1, 5, 5, device=DEV) / 25
+    images = torch.nn.functional.conv2d(images[0], k, padding=2, groups=3)[None]
+    disps = 0.2 + 0.8 * torch.rand(1, n_frames, ht, wd, generator=g, device=DEV)
+    poses = torch.zeros(1, n_frames, 7, device=DEV)
+    poses[..., 6] = 1.0
+    poses[0, :, 0] = 0.03 * torch.arange(n_frames, device=DEV)
+    intr = torch.tensor([100.0, 100.0, wd / 2, ht / 2], device=DEV).view(1, 1, 4).repeat(1, n_frames, 1)
+    return images, poses, disps, intr
+
+
+def test_training_forward_loss_backward_matches_reference_vonet(ext):
+    """ONE training forward/backward (STEPS = 10: eight-frame initialisation + two added frames) of our VONet vs the
+    reference's VONet with the same weights, same clip, same torch / numpy seeds: identical edge bookkeeping and
+    random draws, so trajectories, loss and gradients agree to the fp32 noise of two different op orders."""
+    if not refimport.staged():
+        pytest.skip("oracle/_ref/dpvo_ref_py.zip not staged")
+    from dpvo_b200.train import VONet, sequence_loss
+    from dpvo_b200.lietorch import SE3
+    images, poses, disps, intr = _clip()
+    torch.manual_seed(11)
+    ours = VONet().to(DEV).train()
+    res = {}
+    with refimport.reference_python(native=ext[:3]):
+        import dpvo.net as RN
+        from dpvo.lietorch import SE3 as RSE3
+        theirs = RN.VONet().to(DEV).train()
+        theirs.load_state_dict(ours.state_dict())
+        for name, net, S in (("ref", theirs, RSE3), ("ours", ours, SE3)):
+            torch.manual_seed(21); np.random.seed(21)
+            net.zero_grad()
+            traj = net(images, S(poses).inv(), disps, intr, M=1024, STEPS=10, structure_only=False)
+            loss, _ = sequence_loss([(v, x, y, SE3(P1.data), SE3(P2.data), kl) for v, x, y, P1, P2, kl in traj], 3)
+            loss.backward()
+            res[name] = (loss.item(), [t[1].detach() for t in traj], [t[3].data.detach() for t in traj],
+                         {k: (p.grad.clone() if p.grad is not None else None) for k, p in net.named_parameters()})
+    lr, lo = res["ref"][0], res["ours"][0]
+    print("loss ref %.6f ours %.6f" % (lr, lo))
+    assert len(res["ref"][1]) == len(res["ours"][1]) == 10
+    for i, (a, b) in enumerate(zip(res["ours"][1], res["ref"][1])):
+        assert a.shape == b.shape                                # identical edge sets at every iteration
+    e_first = (res["ours"][1][0] - res["ref"][1][0]).abs().max().item()
+    e_last = (res["ours"][1][-1] - res["ref"][1][-1]).abs().max().item()
+    print("coords abs diff: first iteration %.3g px, last %.3g px" % (e_first, e_last))
+    assert e_first < 1e-2 and abs(lr - lo) <= 2e-2 * abs(lr)
+    cos, worst = [], 0.0
+    gnorm = max(g.norm().item() for g in res["ref"][3].values() if g is not None)
+    for k, gr in res["ref"][3].items():
+        go = res["ours"][3][k]
+        assert (gr is None) == (go is None), k
+        if gr is None:
+            continue
+        worst = max(worst, (gr - go).norm().item() / gnorm)
+        if gr.norm().item() > 1e-3 * gnorm:          # tensors with a real signal (g.bias of SoftAgg has an exactly-zero gradient)
+            cos.append((k, torch.nn.functional.cosine_similarity(gr.flatten().double(), go.flatten().double(), dim=0).item()))
+    low = sorted(cos, key=lambda t: t[1])[:3]
+    print("gradient: worst |ours - ref| / max|ref| = %.3g; cosine over %d tensors with signal: min %s" % (worst, len(cos), low))
+    assert worst < 2e-2 and all(c > 0.99 for _, c in cos)
+
+
+def test_train_step_updates_parameters_and_is_reproducible(ext):
+    from dpvo_b200.train import VONet, TrainStep
+    images, poses, disps, intr = _clip(n_frames=9, seed=5)
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(1); np.random.seed(1)
+        net = VONet().to(DEV).train()
+        before = {k: v.clone() for k, v in net.state_dict().items()}
+        step = TrainStep(net, steps_unrolled=9, total_steps=10000)
+        torch.manual_seed(2); np.random.seed(2)
+        loss, metrics = step(images, poses, disps, intr, structure_only=False)
+        assert torch.isfinite(loss)
+        changed = sum(int(not torch.equal(before[k], v)) for k, v in net.state_dict().items())
+        assert changed > 40
+        outs.append((loss.item(), net.update.c1[0].weight.detach().clone()))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-3 * abs(outs[0][0])
