@@ -606,6 +606,76 @@ std::vector<Tensor> update_heads(Tensor net32, Tensor W4, Tensor b4, c10::option
   return {delta, weight};
 }
 
+// ---- fused layer chains of the update operator (include/dpvo_b200.h, "fused layer chains")
+static void chain_check(const Tensor& t, at::ScalarType st, const char* what) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == st, "dpvo_b200 update chain: ", what, " must be a contiguous CUDA tensor of the expected dtype");
+}
+Tensor update_corr_norm(Tensor corr16, Tensor W0, Tensor W25, Tensor params, Tensor net32, Tensor inp16, c10::optional<Tensor> inp_index,
+                        c10::optional<Tensor> net16_out) {
+  need_cuda(net32, "net");
+  c10::cuda::CUDAGuard guard(net32.device());
+  chain_check(W0, at::kHalf, "W0"); chain_check(W25, at::kHalf, "W25"); chain_check(params, at::kFloat, "params");
+  chain_check(net32, at::kFloat, "net32"); chain_check(inp16, at::kHalf, "inp16");
+  const int64_t E = net32.numel() / 384;
+  Tensor c2 = corr16.reshape({-1, corr16.size(-1)});
+  TORCH_CHECK(c2.scalar_type() == at::kHalf && c2.stride(1) == 1 && c2.size(0) == E && c2.size(1) == 896, "update_corr_norm: corr must be fp16 [E, 896] (zero padded)");
+  TORCH_CHECK(net32.size(-1) == 384 && W0.numel() == 384 * 896 && W25.numel() == 768 * 384 && params.numel() == 7 * 384 && inp16.size(-1) == 384, "update_corr_norm: shapes");
+  Tensor idx;
+  if (inp_index.has_value()) { idx = i64c(*inp_index); TORCH_CHECK(idx.numel() == E, "update_corr_norm: inp_index length"); }
+  else TORCH_CHECK(inp16.numel() == E * 384, "update_corr_norm: inp must have one row per edge when no index is given");
+  Tensor n16 = net16_out.has_value() ? *net16_out : torch::empty({1, E, 384}, net32.options().dtype(at::kHalf));
+  chain_check(n16, at::kHalf, "net16_out");
+  TORCH_CHECK(n16.numel() == E * 384, "update_corr_norm: net16_out shape");
+  check(dpvo_update_corr_norm(c2.data_ptr(), c2.stride(0), W0.data_ptr(), W25.data_ptr(), params.data_ptr<float>(), net32.data_ptr<float>(),
+                              inp16.data_ptr(), idx.defined() ? idx.data_ptr<int64_t>() : nullptr, n16.data_ptr(), E, stream()),
+        "dpvo_b200_ext.update_corr_norm");
+  return n16;
+}
+
+Tensor update_neighbor_mlp(Tensor net16_in, Tensor index, Tensor Wab, Tensor params, Tensor net32, c10::optional<Tensor> net16_out) {
+  need_cuda(net32, "net");
+  c10::cuda::CUDAGuard guard(net32.device());
+  chain_check(net16_in, at::kHalf, "net16_in"); chain_check(Wab, at::kHalf, "Wab"); chain_check(params, at::kFloat, "params"); chain_check(net32, at::kFloat, "net32");
+  const int64_t E = net32.numel() / 384;
+  index = i64c(index);
+  TORCH_CHECK(net32.size(-1) == 384 && net16_in.numel() == E * 384 && index.numel() == E && Wab.numel() == 768 * 384 && params.numel() == 2 * 384, "update_neighbor_mlp: shapes");
+  Tensor n16 = net16_out.has_value() ? *net16_out : torch::empty({1, E, 384}, net32.options().dtype(at::kHalf));
+  chain_check(n16, at::kHalf, "net16_out");
+  TORCH_CHECK(n16.numel() == E * 384, "update_neighbor_mlp: net16_out shape");
+  check(dpvo_update_neighbor_mlp(net16_in.data_ptr(), index.data_ptr<int64_t>(), Wab.data_ptr(), params.data_ptr<float>(), net32.data_ptr<float>(),
+                                 n16.data_ptr(), E, stream()),
+        "dpvo_b200_ext.update_neighbor_mlp");
+  return n16;
+}
+
+std::vector<Tensor> update_gru_heads(Tensor net32, c10::optional<Tensor> hij16, c10::optional<Tensor> group_of, Tensor W6, Tensor params,
+                                     c10::optional<Tensor> coords, c10::optional<Tensor> workspace) {
+  need_cuda(net32, "net");
+  c10::cuda::CUDAGuard guard(net32.device());
+  chain_check(net32, at::kFloat, "net32"); chain_check(W6, at::kHalf, "W6"); chain_check(params, at::kFloat, "params");
+  const int64_t E = net32.numel() / 384;
+  TORCH_CHECK(net32.size(-1) == 384 && W6.numel() == 6 * 384 * 384 && params.numel() == 14 * 384 + 4, "update_gru_heads: shapes");
+  TORCH_CHECK(hij16.has_value() == group_of.has_value(), "update_gru_heads: group rows and group ids come together");
+  Tensor hij, gof;
+  if (hij16.has_value()) {
+    hij = *hij16; gof = group_of->to(at::kInt).contiguous();
+    chain_check(hij, at::kHalf, "hij16");
+    TORCH_CHECK(hij.size(-1) == 384 && gof.numel() == E, "update_gru_heads: group operand shapes");
+  }
+  Tensor cd; int P = 1;
+  if (coords.has_value()) { cd = f32c(*coords); P = cd.size(-1); TORCH_CHECK(cd.numel() == E * 2 * P * P, "update_gru_heads: coords must be [E,2,P,P]"); }
+  const int64_t wsb = dpvo_update_gru_workspace_bytes();
+  Tensor ws = workspace.has_value() ? *workspace : byte_ws(wsb, net32);
+  TORCH_CHECK(ws.is_cuda() && ws.is_contiguous() && (int64_t)(ws.numel() * ws.element_size()) >= wsb, "update_gru_heads: workspace too small");
+  Tensor delta = torch::empty({1, E, 2}, net32.options()), weight = torch::empty({1, E, 2}, net32.options());
+  check(dpvo_update_gru_heads(net32.data_ptr<float>(), hij.defined() ? hij.data_ptr() : nullptr, gof.defined() ? gof.data_ptr<int>() : nullptr,
+                              W6.data_ptr(), params.data_ptr<float>(), cd.defined() ? cd.data_ptr<float>() : nullptr, P,
+                              delta.data_ptr<float>(), weight.data_ptr<float>(), ws.data_ptr(), E, stream()),
+        "dpvo_b200_ext.update_gru_heads");
+  return {delta, weight};
+}
+int64_t update_gru_workspace_bytes() { return dpvo_update_gru_workspace_bytes(); }
+
 int64_t launch_count() { return dpvo_launch_count(); }
 std::string version() { return dpvo_version(); }
 
@@ -667,6 +737,13 @@ PYBIND11_MODULE(dpvo_b200_ext, m) {
   m.def("linear_f16", &linear_f16, "tcgen05 dense layer", py::arg("x"), py::arg("w"), py::arg("bias") = py::none(),
         py::arg("epilogue") = 0, py::arg("res") = py::none(), py::arg("gate") = py::none(), py::arg("gather") = py::none(),
         py::arg("out_f32") = false, py::arg("out") = py::none(), py::arg("out16") = py::none());
+  m.def("update_corr_norm", &update_corr_norm, "fused corr MLP + context add + LayerNorm (net.py:76-77)", py::arg("corr16"), py::arg("W0"), py::arg("W25"),
+        py::arg("params"), py::arg("net32"), py::arg("inp16"), py::arg("inp_index") = py::none(), py::arg("net16_out") = py::none());
+  m.def("update_neighbor_mlp", &update_neighbor_mlp, "fused masked neighbour gather + 2-layer MLP + residual (net.py:83-85)", py::arg("net16_in"), py::arg("index"),
+        py::arg("Wab"), py::arg("params"), py::arg("net32"), py::arg("net16_out") = py::none());
+  m.def("update_gru_heads", &update_gru_heads, "fused group add + GRU + heads (net.py:88-92)", py::arg("net32"), py::arg("hij16"), py::arg("group_of"),
+        py::arg("W6"), py::arg("params"), py::arg("coords") = py::none(), py::arg("workspace") = py::none());
+  m.def("update_gru_workspace_bytes", &update_gru_workspace_bytes, "scratch bytes of update_gru_heads");
   m.def("neighbors_from_groups", &neighbors_from_groups, "temporal neighbours from a kk/jj grouping");
   m.def("launch_count", &launch_count, "kernel launches issued by libdpvo_b200 so far");
   m.def("version", &version, "library version string");

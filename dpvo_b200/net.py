@@ -151,6 +151,22 @@ class Update(nn.Module):
             # gate and first residual layer share their input: one GEMM with N = 768 (sigmoid | relu halves)
             (wg, bg), (wa, ba) = P["gr%d_g" % i], P["gr%d_a" % i]
             P["gr%d_ga" % i] = (torch.cat([wg, wa], 0).contiguous(), torch.cat([bg, ba], 0).contiguous())
+        # fused layer chains (csrc/chain.cu): stacked fp16 weights and one fp32 parameter block per chain
+        def f32cat(*ts):
+            return torch.cat([t.detach().float().reshape(-1) for t in ts]).contiguous()
+        P["A_W0"] = P["corr0"][0]
+        P["A_W25"] = torch.cat([P["corr2"][0], P["corr5"][0]], 0).contiguous()
+        P["A_p"] = f32cat(self.corr[0].bias, self.corr[2].bias, self.corr[3].weight, self.corr[3].bias, self.corr[5].bias,
+                          self.norm.weight, self.norm.bias)
+        for nm, mlp in (("C1", self.c1), ("C2", self.c2)):
+            P[nm + "_W"] = torch.cat([mlp[0].weight, mlp[2].weight], 0).detach().half().contiguous()
+            P[nm + "_p"] = f32cat(mlp[0].bias, mlp[2].bias)
+        g1, g3 = self.gru[1], self.gru[3]
+        P["G_W6"] = torch.cat([g1.gate[0].weight, g1.res[0].weight, g1.res[2].weight,
+                               g3.gate[0].weight, g3.res[0].weight, g3.res[2].weight], 0).detach().half().contiguous()
+        P["G_p"] = f32cat(self.gru[0].weight, self.gru[0].bias, g1.gate[0].bias, g1.res[0].bias, g1.res[2].bias,
+                          self.gru[2].weight, self.gru[2].bias, g3.gate[0].bias, g3.res[0].bias, g3.res[2].bias,
+                          self.d[1].weight, self.w[1].weight, self.d[1].bias, self.w[1].bias)
         P["heads_w"] = torch.cat([self.d[1].weight, self.w[1].weight], 0).detach().float().contiguous()
         P["heads_b"] = torch.cat([self.d[1].bias, self.w[1].bias], 0).detach().float().contiguous()
         self._packed = P
@@ -198,7 +214,44 @@ class Update(nn.Module):
             groups_kk = EdgeGroups(kk, None, jj)
         elif groups_ij is None:
             groups_ij = EdgeGroups(ii, jj, None)
+        if getattr(self, "fused_chains", True):
+            return self._forward_chains(net, inp, corr, groups_kk, groups_ij)
         return self._forward_tcgen05(net, inp, corr, groups_kk, groups_ij)
+
+    def _forward_chains(self, net, inp, corr, groups_kk, groups_ij):
+        """The row-local stretches of net.py:74-92 as one tcgen05 chain kernel each (csrc/chain.cu): corr MLP + context
+        add + LayerNorm; c1 and c2 on the masked temporal neighbours; group add + GRU + heads.  Between them only the two
+        SoftAgg reductions (which mix rows of a group) run as separate kernels."""
+        ex = extensions()[3]
+        P = self.packed()
+        inplace = net.dtype == torch.float32 and net.is_contiguous() and self.inplace_state
+        net32 = net if inplace else net.float().contiguous().clone()
+        inp16 = inp if inp.dtype == torch.half else inp.half()
+        inp16 = inp16.reshape(-1, DIM).contiguous()
+        gev = getattr(self, "gemm_events", None)          # bench.py: CUDA events around every tensor-core launch
+
+        def timed(f, *args):
+            if gev is None:
+                return f(*args)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = f(*args)
+            e1.record()
+            gev.append((e0, e1))
+            return y
+
+        def L(x, name):
+            return timed(ex.linear_f16, x, P[name][0], P[name][1], 0)
+        n16 = timed(ex.update_corr_norm, corr, P["A_W0"], P["A_W25"], P["A_p"], net32, inp16, self._inp_index)
+        ix, jx = ex.neighbors_from_groups(groups_kk.order, groups_kk.group_of)
+        n16b = timed(ex.update_neighbor_mlp, n16, ix, P["C1_W"], P["C1_p"], net32)
+        n16 = timed(ex.update_neighbor_mlp, n16b, jx, P["C2_W"], P["C2_p"], net32, n16)
+        y = ex.softagg_reduce(L(n16, "fg_kk"), groups_kk.order, groups_kk.group_start, groups_kk.n, groups_kk.max_groups)
+        n16 = ex.residual_add_(net32, L(y, "h_kk"), groups_kk.group_of, True)
+        y = ex.softagg_reduce(L(n16, "fg_ij"), groups_ij.order, groups_ij.group_start, groups_ij.n, groups_ij.max_groups)
+        h_ij = L(y, "h_ij")
+        delta, weight = timed(ex.update_gru_heads, net32, h_ij.reshape(-1, DIM), groups_ij.group_of, P["G_W6"], P["G_p"], self._coords)
+        return net32, (delta, weight, None)
 
     def _forward_tcgen05(self, net, inp, corr, groups_kk, groups_ij):
         """every dense layer on dpvo_linear_f16, with the gather / residual / gating fused into the

@@ -408,6 +408,38 @@ int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather, const voi
                     void* Y16, int64_t ldy16,
                     int64_t rows, int N, int K, int epilogue, void* stream);
 
+/* ---- Update operator, fused layer chains (dpvo_b200/csrc/chain.cu) -------------------------------------------------
+ * The row-local stretches of Update.forward (dpvo/net.py:74-92) as one tcgen05 kernel each: a 128-edge tile runs
+ * through every dense layer of the stretch on chip (operand tile in shared memory, fp32 accumulator in TMEM),
+ * LayerNorm / gating / heads in the epilogues.  DIM = 384 (net.py:24), E = edges, all weights fp16 row-major
+ * [out, in], all parameters fp32, `net32` is the fp32 recurrent state [E, 384] updated IN PLACE.
+ *
+ * dpvo_update_corr_norm   (net.py:76-77, corr = net.py:66-72)
+ *     net32 <- LN_norm( net32 + inp16[inp_index ? inp_index[e] : e] + corr.5( relu( LN_corr.3( corr.2( relu( corr.0(corr16) ) ) ) ) ) )
+ *     corr16 [E, 896] fp16 (882 correlation features zero padded to 896; row stride ld_corr halves), W0 = corr.0.weight padded
+ *     to [384, 896], W25 = rows of corr.2.weight then corr.5.weight [768, 384],
+ *     params = corr.0.bias | corr.2.bias | corr.3.weight | corr.3.bias | corr.5.bias | norm.weight | norm.bias (7 x 384).
+ *     net16 [E, 384] receives the fp16 copy of the new state (operand of the next layer).
+ * dpvo_update_neighbor_mlp  (net.py:83-85, one call for c1 with ix and one for c2 with jx)
+ *     net32 <- net32 + c.2( relu( c.0( mask * net16_in[index] ) ) ),  index[e] = -1 masks the row (mask = 0)
+ *     Wab = rows of c.0.weight then c.2.weight [768, 384], params = c.0.bias | c.2.bias.  net16_out != net16_in.
+ * dpvo_update_gru_heads  (net.py:88-92, blocks.py:15-29)
+ *     x = LN_gru.0( net32 + hij16[group_of[e]] );  y = x + gate1(x) * res1(x);  z = LN_gru.2(y);  net32 <- z + gate2(z) * res2(z)
+ *     delta = d(net32) (+ centre of coords when given: the BA target of dpvo.py:341), weight = w(net32)
+ *     W6 = rows of gru.1.gate.0 | gru.1.res.0 | gru.1.res.2 | gru.3.gate.0 | gru.3.res.0 | gru.3.res.2 weights [2304, 384],
+ *     params = gru.0.weight | gru.0.bias | b(gate1) | b(res1.0) | b(res1.2) | gru.2.weight | gru.2.bias | b(gate2) | b(res2.0) |
+ *              b(res2.2) | d.1.weight[2,384] | w.1.weight[2,384] | d.1.bias[2] | w.1.bias[2]          (14 x 384 + 4 floats)
+ *     hij16 [G, 384] fp16 / group_of int32 [E] may both be NULL (nothing added).  coords [E, 2, P, P] fp32 or NULL.
+ *     delta, weight [E, 2] fp32.  workspace: dpvo_update_gru_workspace_bytes() bytes (row-private scratch, L2 resident).
+ */
+int dpvo_update_corr_norm(const void* corr16, int64_t ld_corr, const void* W0, const void* W25, const float* params,
+                          float* net32, const void* inp16, const int64_t* inp_index, void* net16, int64_t E, void* stream);
+int dpvo_update_neighbor_mlp(const void* net16_in, const int64_t* index, const void* Wab, const float* params,
+                             float* net32, void* net16_out, int64_t E, void* stream);
+int64_t dpvo_update_gru_workspace_bytes(void);
+int dpvo_update_gru_heads(float* net32, const void* hij16, const int32_t* group_of, const void* W6, const float* params,
+                          const float* coords, int P, float* delta, float* weight, void* workspace, int64_t E, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
