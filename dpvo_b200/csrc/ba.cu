@@ -46,6 +46,8 @@ struct BaArgs {
   float* uk;      // [M]
   float* rec;     // [Gp][90]
   float* dX;      // [6N]
+  float* part;    // [n_part][6N(6N+3)/2] per-CTA partial reduced systems (fast path), NULL = the solve cluster forms S itself
+  int n_part;
   long long* dbg; // optional phase timestamps of the solve kernel (cluster rank 0), NULL = off
 };
 
@@ -59,19 +61,41 @@ __device__ __forceinline__ void linearize_edge(const BaArgs& a, int64_t e, float
 // kernel A: per-pair and per-patch reductions
 // ==========================================================================================
 constexpr int BA_RED_WARPS = 4;
+constexpr int BA_FAST_WARPS = 16;     // fast path: warps per CTA, each with a private copy of the reduced system
+constexpr int BA_FAST_MAX_N = 12;     // 16 packed copies (upper triangle + gradient, 6N(6N+3)/2 floats) fit in shared memory up to here
+__host__ __device__ constexpr int ba_packed_entries(int N6) { return N6 * (N6 + 1) / 2 + N6; }
+// packed upper triangle, row-major: entry (r, c), r <= c
+__device__ __forceinline__ int ba_tri(int N6, int r, int c) { return r * N6 - (r * (r - 1)) / 2 + (c - r); }
 
-__global__ void __launch_bounds__(BA_RED_WARPS * 32)
+// SYSTEM = false: pair records and patch rows go to global memory, the solve cluster forms the reduced system.
+// SYSTEM = true (0 < N <= BA_FAST_MAX_N, the sliding-window case): every warp also applies its items to a private
+// copy of the reduced pose system  S = B - E Q E^T,  y = v - E Q u  (upper triangle; row 6N = y) in shared memory --
+// the Schur rank-1 update of a patch right after its row E_k is formed, the 6x6 pose blocks of a pair right after its
+// record is summed -- so that this work runs on every SM instead of inside the 8-CTA solve cluster.  Items are dealt
+// to warps statically, a warp applies its items in order, the copies of a CTA are added in warp order and the CTAs'
+// partial systems are summed in CTA order by the solve kernel: still no float atomics, still bit-reproducible.
+// A copy is stored packed (upper triangle row-major, then the gradient): 7.4 KB for 10 free poses.
+template <bool SYSTEM>
+__global__ void __launch_bounds__((SYSTEM ? BA_FAST_WARPS : BA_RED_WARPS) * 32)
 ba_reduce_kernel(const BaArgs a) {
-  __shared__ float ek_all[BA_RED_WARPS][6 * BA_MAX_N];
+  constexpr int WARPS = SYSTEM ? BA_FAST_WARPS : BA_RED_WARPS;
+  extern __shared__ __align__(16) float red_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float* ek = ek_all[wib];
+  float* ek = red_smem + wib * (6 * BA_MAX_N);
+  const int n_ent = ba_packed_entries(6 * a.N);
+  float* recw = red_smem + WARPS * (6 * BA_MAX_N) + wib * 96;                         // SYSTEM: this warp's pair record
+  float* Sw = red_smem + WARPS * (6 * BA_MAX_N + 96) + (size_t)wib * n_ent;           // SYSTEM: this warp's copy, [6N+1][6N]
+  if constexpr (SYSTEM) {
+    for (int i = lane; i < n_ent; i += 32) Sw[i] = 0.0f;
+    __syncwarp();
+  }
   const float fx = a.intrinsics[0], fy = a.intrinsics[1], cx = a.intrinsics[2], cy = a.intrinsics[3];
   const float lm = a.lmbda[0];
   const int Gk = *a.k_n, Gp = (a.N > 0) ? *a.p_n : 0;
   const int N = a.N, N6 = 6 * a.N;
-  const int nwarps = gridDim.x * BA_RED_WARPS;
+  const int nwarps = gridDim.x * WARPS;
 
-  for (int item = blockIdx.x * BA_RED_WARPS + wib; item < Gk + Gp; item += nwarps) {
+  for (int item = blockIdx.x * WARPS + wib; item < Gk + Gp; item += nwarps) {
     if (item < Gk) {
       // ------------------------------------------------------------ patch item
       const int g = item;
@@ -138,7 +162,22 @@ ba_reduce_kernel(const BaArgs a) {
       }
       __syncwarp();
       for (int i = lane; i < N6; i += 32) a.Ed[(int64_t)g * N6 + i] = ek[i];
-      if (lane == 0) { a.Qk[g] = 1.0f / (Csum + lm); a.uk[g] = usum; }
+      const float qk = 1.0f / (Csum + lm);
+      if (lane == 0) { a.Qk[g] = qk; a.uk[g] = usum; }
+      if constexpr (SYSTEM) {
+        // S -= Q_k E_k E_k^T (upper triangle), y -= Q_k u_k E_k: lanes stride the columns of a row; rows are independent
+        // read-modify-writes of disjoint addresses, unrolled so that their shared-memory latencies overlap
+        __syncwarp();
+        int base = 0;
+#pragma unroll 4
+        for (int r = 0; r < N6; ++r) {
+          const float er = qk * ek[r];
+          float* srow = Sw + base - r;                          // srow[c] = entry (r, c)
+          for (int c = r + lane; c < N6; c += 32) srow[c] -= er * ek[c];
+          base += N6 - r;
+        }
+        for (int c = lane; c < N6; c += 32) Sw[base + c] -= qk * usum * ek[c];
+      }
       __syncwarp();
     } else {
       // ------------------------------------------------------------ pair item
@@ -178,10 +217,59 @@ ba_reduce_kernel(const BaArgs a) {
         const float s = warp_sum(acc[k]);
         if ((k & 31) == lane) mine[k >> 5] = s;
       }
-      float* rp = a.rec + (int64_t)p * BA_REC;
-      rp[lane] = mine[0];
-      rp[32 + lane] = mine[1];
-      if (64 + lane < BA_REC) rp[64 + lane] = mine[2];
+      if constexpr (!SYSTEM) {
+        float* rp = a.rec + (int64_t)p * BA_REC;
+        rp[lane] = mine[0];
+        rp[32 + lane] = mine[1];
+        if (64 + lane < BA_REC) rp[64 + lane] = mine[2];
+      } else {
+        // the record goes straight into this warp's system: every entry of S is owned by one (virtual) thread id of
+        // the 63 below for the whole record, as in the solve kernel's assembly (diagonal blocks: id (x,y) serves the
+        // source- and the target-pose block; off-diagonal blocks are stored for the ordered pose pair)
+        recw[lane] = mine[0];
+        recw[32 + lane] = mine[1];
+        if (64 + lane < BA_REC) recw[64 + lane] = mine[2];
+        __syncwarp();
+        const long long fi = a.p_key_i[p] - a.t0, fj = a.p_key_j[p] - a.t0;
+        const int bi = (fi >= 0 && fi < N) ? (int)fi : -1, bj = (fj >= 0 && fj < N) ? (int)fj : -1;
+        for (int id = lane; id < 63; id += 32) {
+          const float* rc = recw;
+          if (id < 21) {
+            int x = 0, rem = id;
+            while (rem >= 6 - x) { rem -= 6 - x; ++x; }
+            const int y = x + rem;
+            if (bi >= 0) {
+              float v = rc[id];
+              if (bi == bj) v += rc[57 + id] + rc[21 + x * 6 + y] + rc[21 + y * 6 + x];   // self edge i -> i
+              Sw[ba_tri(N6, 6 * bi + x, 6 * bi + y)] += v;
+            }
+            if (bj >= 0 && bi != bj) Sw[ba_tri(N6, 6 * bj + x, 6 * bj + y)] += rc[57 + id];
+          } else if (id < 57) {
+            const int e = id - 21, x = e / 6, y = e - 6 * x;
+            if (bi >= 0 && bj >= 0 && bi != bj) {
+              if (bi < bj) Sw[ba_tri(N6, 6 * bi + x, 6 * bj + y)] += rc[21 + x * 6 + y];
+              else Sw[ba_tri(N6, 6 * bj + x, 6 * bi + y)] += rc[21 + y * 6 + x];
+            }
+          } else {
+            const int c = id - 57;
+            if (bi >= 0) Sw[N6 * (N6 + 1) / 2 + 6 * bi + c] += rc[78 + c] + ((bi == bj) ? rc[84 + c] : 0.0f);
+            if (bj >= 0 && bi != bj) Sw[N6 * (N6 + 1) / 2 + 6 * bj + c] += rc[84 + c];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if constexpr (SYSTEM) {
+    // the CTA's partial system: copies added in warp order, one entry per thread
+    __syncthreads();
+    const float* S0 = red_smem + WARPS * (6 * BA_MAX_N + 96);
+    float* out = a.part + (int64_t)blockIdx.x * n_ent;
+    for (int i = threadIdx.x; i < n_ent; i += WARPS * 32) {
+      float v = S0[i];
+#pragma unroll
+      for (int w = 1; w < WARPS; ++w) v += S0[(size_t)w * n_ent + i];
+      out[i] = v;
     }
   }
 }
@@ -228,7 +316,31 @@ ba_solve_kernel(const BaArgs a) {
 #define BA_STAMP(i) do { if (a.dbg && rank == 0 && tid == 0) a.dbg[i] = clock64(); } while (0)
   BA_STAMP(0);
 
-  if (N > 0) {
+  if (N > 0 && a.part) {
+    // ---- 1 (fast path). The reduced system arrives as per-CTA partial sums from ba_reduce_kernel<true>: the cluster
+    // adds them in CTA order, one entry per thread, 32 loads in flight, and deposits the sums in CTA 0's shared memory.
+    SolveSmem* root = cluster.map_shared_rank(&sm, 0);
+    const int n_ent = ba_packed_entries(N6), n_tri = N6 * (N6 + 1) / 2;
+    for (int e = rank * BA_SOLVE_THREADS + tid; e < n_ent; e += BA_CLUSTER * BA_SOLVE_THREADS) {
+      int row = N6, col = e - n_tri;                              // gradient entries follow the packed triangle
+      if (e < n_tri) {
+        int rem = e;
+        row = 0;
+        while (rem >= N6 - row) { rem -= N6 - row; ++row; }
+        col = row + rem;
+      }
+      float s = 0.0f;
+      for (int c0 = 0; c0 < a.n_part; c0 += 32) {
+        float v[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] = (c0 + u < a.n_part) ? __ldcg(a.part + (int64_t)(c0 + u) * n_ent + e) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) s += v[u];
+      }
+      root->S[row][col] = s;
+    }
+    BA_STAMP(1);
+  } else if (N > 0) {
     for (int o = tid; o < (N6 + 1) * N6; o += BA_SOLVE_THREADS) sm.S[o / N6][o % N6] = 0.0f;
     __syncthreads();
     // ---- 1a. Schur products over this CTA's patches.  Rows are staged as sqrt(Q_k) [E_k | u_k | 0..]: the gradient
@@ -391,7 +503,7 @@ ba_solve_kernel(const BaArgs a) {
       const int row = o / N6, col = o - row * N6;
       if (row < N6 && row > col) continue;
       float s = sm.S[row][col];
-      for (int r = 1; r < BA_CLUSTER; ++r) s += cluster.map_shared_rank(&sm, r)->S[row][col];
+      if (!a.part) for (int r = 1; r < BA_CLUSTER; ++r) s += cluster.map_shared_rank(&sm, r)->S[row][col];
       if (row == col) s += 1e-4f * s + 1.0f;            // S += I * (1e-4 * S + 1)   ba_cuda.cu:560
       sm.S[row][col] = s;
       if (row < N6) sm.S[col][row] = s;
@@ -676,8 +788,22 @@ static int ba_run(BaArgs& a, int iterations, cudaStream_t st) {
     if (e != cudaSuccess) return check_cuda(e, "ba_forward: cudaFuncSetAttribute");
   }
   const int red_blocks = sm_count() * 4;
+  // sliding-window sizes: the reduced system is assembled by the reduce kernel (one partial per CTA, stored where the
+  // pair records of the general path would go -- the fast path does not materialise them)
+  a.part = nullptr; a.n_part = 0;
+  if (a.N > 0 && a.N <= BA_FAST_MAX_N && (int64_t)sm_count() * ba_packed_entries(6 * a.N) <= a.E * (int64_t)BA_REC) {
+    a.part = a.rec;
+    a.n_part = sm_count();
+  }
+  const bool fast = a.part != nullptr;
+  const size_t fast_smem = fast ? (size_t)BA_FAST_WARPS * (6 * BA_MAX_N + 96 + (size_t)ba_packed_entries(6 * a.N)) * sizeof(float) : 0;
+  if (fast) {
+    cudaError_t e = cudaFuncSetAttribute(ba_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem);
+    if (e != cudaSuccess) return check_cuda(e, "ba_forward: cudaFuncSetAttribute (reduce)");
+  }
   for (int it = 0; it < iterations; ++it) {
-    ba_reduce_kernel<<<red_blocks, BA_RED_WARPS * 32, 0, st>>>(a);
+    if (fast) ba_reduce_kernel<true><<<a.n_part, BA_FAST_WARPS * 32, fast_smem, st>>>(a);
+    else ba_reduce_kernel<false><<<red_blocks, BA_RED_WARPS * 32, BA_RED_WARPS * 6 * BA_MAX_N * sizeof(float), st>>>(a);
     DPVO_LAUNCH_CHECK("ba_reduce_kernel");
     ba_solve_kernel<<<BA_CLUSTER, BA_SOLVE_THREADS, sizeof(SolveSmem), st>>>(a);
     DPVO_LAUNCH_CHECK("ba_solve_kernel");
