@@ -676,6 +676,61 @@ std::vector<Tensor> update_gru_heads(Tensor net32, c10::optional<Tensor> hij16, 
 }
 int64_t update_gru_workspace_bytes() { return dpvo_update_gru_workspace_bytes(); }
 
+// ---- device-resident patch-graph bookkeeping (include/dpvo_b200.h)
+static void pg_check(const Tensor& ii, const Tensor& jj, const Tensor& kk, const Tensor& active) {
+  TORCH_CHECK(ii.is_cuda() && ii.scalar_type() == at::kLong && ii.is_contiguous() && jj.scalar_type() == at::kLong && jj.is_contiguous() &&
+              kk.scalar_type() == at::kLong && kk.is_contiguous() && active.scalar_type() == at::kByte && active.is_contiguous() &&
+              jj.numel() == ii.numel() && kk.numel() == ii.numel() && active.numel() == ii.numel(), "pgraph: ii / jj / kk int64 and active uint8, one entry per slot");
+}
+void pgraph_remove(Tensor ii, Tensor jj, Tensor kk, Tensor active, int64_t rule, Tensor frame, int64_t param, c10::optional<Tensor> enable,
+                   int64_t dummy_frame, int64_t dummy_patch, int64_t M, Tensor n_active) {
+  need_cuda(ii, "ii");
+  c10::cuda::CUDAGuard guard(ii.device());
+  pg_check(ii, jj, kk, active);
+  TORCH_CHECK(frame.is_cuda() && frame.scalar_type() == at::kLong && frame.numel() == 1 && n_active.is_cuda() && n_active.scalar_type() == at::kInt && n_active.numel() == 1,
+              "pgraph_remove: frame is a device int64 scalar, n_active a device int32 scalar");
+  const int32_t* en = nullptr;
+  if (enable.has_value()) { TORCH_CHECK(enable->is_cuda() && enable->scalar_type() == at::kInt && enable->numel() == 1, "pgraph_remove: enable is a device int32 scalar"); en = enable->data_ptr<int>(); }
+  check(dpvo_pgraph_remove(ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), kk.data_ptr<int64_t>(), active.data_ptr<uint8_t>(), ii.numel(), (int)rule,
+                           frame.data_ptr<int64_t>(), param, en, dummy_frame, dummy_patch, (int)M, n_active.data_ptr<int>(), stream()),
+        "dpvo_b200_ext.pgraph_remove");
+}
+Tensor pgraph_append(Tensor ii, Tensor jj, Tensor kk, Tensor active, Tensor new_ii, Tensor new_jj, Tensor new_kk, c10::optional<Tensor> enable,
+                     c10::optional<Tensor> state, Tensor n_active, Tensor overflow) {
+  need_cuda(ii, "ii");
+  c10::cuda::CUDAGuard guard(ii.device());
+  pg_check(ii, jj, kk, active);
+  new_ii = i64c(new_ii); new_jj = i64c(new_jj); new_kk = i64c(new_kk);
+  const int64_t n_new = new_ii.numel();
+  TORCH_CHECK(new_jj.numel() == n_new && new_kk.numel() == n_new, "pgraph_append: new edge lists differ in length");
+  TORCH_CHECK(n_active.is_cuda() && n_active.scalar_type() == at::kInt && n_active.numel() == 1 && overflow.is_cuda() && overflow.scalar_type() == at::kInt && overflow.numel() == 1,
+              "pgraph_append: n_active / overflow are device int32 scalars");
+  const int32_t* en = nullptr;
+  if (enable.has_value()) { TORCH_CHECK(enable->is_cuda() && enable->scalar_type() == at::kInt && enable->numel() == 1, "pgraph_append: enable is a device int32 scalar"); en = enable->data_ptr<int>(); }
+  Tensor slots = torch::empty({n_new}, ii.options().dtype(at::kInt));
+  float* st = nullptr;
+  if (state.has_value()) {
+    TORCH_CHECK(state->is_cuda() && state->scalar_type() == at::kFloat && state->is_contiguous() && state->numel() == ii.numel() * 384,
+                "pgraph_append: state must be the contiguous fp32 [cap, 384] recurrent state");
+    st = state->data_ptr<float>();
+  }
+  check(dpvo_pgraph_append(ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), kk.data_ptr<int64_t>(), active.data_ptr<uint8_t>(), ii.numel(),
+                           new_ii.data_ptr<int64_t>(), new_jj.data_ptr<int64_t>(), new_kk.data_ptr<int64_t>(), n_new, en, st, slots.data_ptr<int>(),
+                           n_active.data_ptr<int>(), overflow.data_ptr<int>(), stream()),
+        "dpvo_b200_ext.pgraph_append");
+  return slots;
+}
+std::vector<Tensor> pgraph_new_edges(Tensor n_dev, int64_t M, int64_t r) {
+  need_cuda(n_dev, "n");
+  c10::cuda::CUDAGuard guard(n_dev.device());
+  TORCH_CHECK(n_dev.scalar_type() == at::kLong && n_dev.numel() == 1, "pgraph_new_edges: n is a device int64 scalar");
+  const int64_t total = M * (2 * r - 1);
+  Tensor ii = torch::empty({total}, n_dev.options()), jj = torch::empty({total}, n_dev.options()), kk = torch::empty({total}, n_dev.options());
+  check(dpvo_pgraph_new_edges(n_dev.data_ptr<int64_t>(), (int)M, (int)r, ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), kk.data_ptr<int64_t>(), stream()),
+        "dpvo_b200_ext.pgraph_new_edges");
+  return {ii, jj, kk};
+}
+
 int64_t launch_count() { return dpvo_launch_count(); }
 std::string version() { return dpvo_version(); }
 
@@ -744,6 +799,11 @@ PYBIND11_MODULE(dpvo_b200_ext, m) {
   m.def("update_gru_heads", &update_gru_heads, "fused group add + GRU + heads (net.py:88-92)", py::arg("net32"), py::arg("hij16"), py::arg("group_of"),
         py::arg("W6"), py::arg("params"), py::arg("coords") = py::none(), py::arg("workspace") = py::none());
   m.def("update_gru_workspace_bytes", &update_gru_workspace_bytes, "scratch bytes of update_gru_heads");
+  m.def("pgraph_remove", &pgraph_remove, "park edges by rule on the fixed-capacity edge store", py::arg("ii"), py::arg("jj"), py::arg("kk"), py::arg("active"),
+        py::arg("rule"), py::arg("frame"), py::arg("param"), py::arg("enable"), py::arg("dummy_frame"), py::arg("dummy_patch"), py::arg("M"), py::arg("n_active"));
+  m.def("pgraph_append", &pgraph_append, "fill parked slots with new edges", py::arg("ii"), py::arg("jj"), py::arg("kk"), py::arg("active"), py::arg("new_ii"),
+        py::arg("new_jj"), py::arg("new_kk"), py::arg("enable"), py::arg("state"), py::arg("n_active"), py::arg("overflow"));
+  m.def("pgraph_new_edges", &pgraph_new_edges, "steady-state forward + backward edges of the newest frame");
   m.def("neighbors_from_groups", &neighbors_from_groups, "temporal neighbours from a kk/jj grouping");
   m.def("launch_count", &launch_count, "kernel launches issued by libdpvo_b200 so far");
   m.def("version", &version, "library version string");

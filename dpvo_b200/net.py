@@ -10,8 +10,9 @@ Data flow is fp32 for the carried state `net`, fp16 for every GEMM operand (what
 autocast does, dpvo.py:332), with the fp16 copies produced inside the fused row kernels.  The edge
 groupings come from ONE device radix-sort launch each (no host sync, no torch.unique, no D2H sort).
 
-Every dense layer runs on the tcgen05 kernel of include/dpvo_b200.h (dpvo_linear_f16); there is no library
-GEMM and no other backend in the product (a cuBLAS comparison lives in tools/bench_gemm.py only).
+Every dense layer runs on hand-written tcgen05 kernels (csrc/chain.cu: the three fused layer chains; csrc/gemm.cu:
+dpvo_linear_f16 for the four SoftAgg layers); there is no library GEMM and no other backend in the product (a cuBLAS
+comparison lives in tools/bench_gemm.py only).
 """
 import torch
 import torch.nn as nn
@@ -214,9 +215,7 @@ class Update(nn.Module):
             groups_kk = EdgeGroups(kk, None, jj)
         elif groups_ij is None:
             groups_ij = EdgeGroups(ii, jj, None)
-        if getattr(self, "fused_chains", True):
-            return self._forward_chains(net, inp, corr, groups_kk, groups_ij)
-        return self._forward_tcgen05(net, inp, corr, groups_kk, groups_ij)
+        return self._forward_chains(net, inp, corr, groups_kk, groups_ij)
 
     def _forward_chains(self, net, inp, corr, groups_kk, groups_ij):
         """The row-local stretches of net.py:74-92 as one tcgen05 chain kernel each (csrc/chain.cu): corr MLP + context
@@ -252,53 +251,3 @@ class Update(nn.Module):
         h_ij = L(y, "h_ij")
         delta, weight = timed(ex.update_gru_heads, net32, h_ij.reshape(-1, DIM), groups_ij.group_of, P["G_W6"], P["G_p"], self._coords)
         return net32, (delta, weight, None)
-
-    def _forward_tcgen05(self, net, inp, corr, groups_kk, groups_ij):
-        """every dense layer on dpvo_linear_f16, with the gather / residual / gating fused into the
-        operand load and the epilogue"""
-        ex = extensions()[3]
-        P = self.packed()
-        NONE, RELU, SIGM, RESADD, GATED, SIGM_RELU = 0, 1, 2, 3, 4, 5
-
-        gev = getattr(self, "gemm_events", None)          # bench.py: CUDA events around every dense-layer launch
-
-        def L(x, name, epi=NONE, **kw):
-            wgt, b = P[name]
-            if gev is None:
-                return ex.linear_f16(x, wgt, b, epi, **kw)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            y = ex.linear_f16(x, wgt, b, epi, **kw)
-            e1.record()
-            gev.append((e0, e1))
-            return y
-
-        h = L(L(corr, "corr0", RELU), "corr2")
-        _, h = ex.add_layernorm(h, None, None, self.corr[3].weight, self.corr[3].bias, 1e-3, True, False, True)
-        h = L(h, "corr5")
-        # the fp32 state is updated in place when the caller hands one in (contiguous fp32): the recurrent `net` then
-        # lives in a single buffer across updates
-        inplace = net.dtype == torch.float32 and net.is_contiguous() and self.inplace_state
-        net32, n16 = ex.add_layernorm(net, inp, h, self.norm.weight, self.norm.bias, 1e-3, False, True, True, self._inp_index, inplace)
-        ix, jx = ex.neighbors_from_groups(groups_kk.order, groups_kk.group_of)
-        for idx, a, b in ((ix, "c1a", "c1b"), (jx, "c2a", "c2b")):
-            u = L(n16, a, RELU, gather=idx)                       # c(mask * net[idx]) first layer
-            n16 = torch.empty_like(n16)
-            L(u, b, RESADD, res=net32, out_f32=True, out=net32, out16=n16)   # net += second layer
-        y = ex.softagg_reduce(L(n16, "fg_kk"), groups_kk.order, groups_kk.group_start, groups_kk.n, groups_kk.max_groups)
-        n16 = ex.residual_add_(net32, L(y, "h_kk"), groups_kk.group_of, True)
-        y = ex.softagg_reduce(L(n16, "fg_ij"), groups_ij.order, groups_ij.group_start, groups_ij.n, groups_ij.max_groups)
-        h_ij = L(y, "h_ij")
-        # GRU (net.py:43-52): LN, GatedResidual, LN, GatedResidual.  Each GatedResidual x + gate * res is applied by
-        # the pass that consumes it (the second LayerNorm; the heads), so its last dense layer is a plain GEMM and
-        # the fp32 state is read and written once less per block.
-        x32 = net32
-        # net += h_ij[group] and the first LayerNorm in one pass: the un-normalised sum is not needed again (net.py:88-90)
-        x32, x16 = ex.add_layernorm(x32, h_ij, None, self.gru[0].weight, self.gru[0].bias, 1e-3, False, True, True, groups_ij.group_of.long(), True)
-        ga = L(x16, "gr1_ga", SIGM_RELU)                           # [1, E, 768] = [sigmoid gate | relu(res layer 1)]
-        r2 = L(ga[..., DIM:], "gr1_b")
-        x32, x16 = ex.add_layernorm(x32, None, r2, self.gru[2].weight, self.gru[2].bias, 1e-3, False, True, True, None, True, ga[..., :DIM])
-        ga = L(x16, "gr3_ga", SIGM_RELU)
-        r2 = L(ga[..., DIM:], "gr3_b")
-        delta, weight = ex.update_heads(x32, P["heads_w"], P["heads_b"], self._coords, ga[..., :DIM], r2)    # x32 <- x32 + gate * res
-        return x32, (delta, weight, None)

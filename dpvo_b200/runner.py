@@ -16,8 +16,13 @@ from .net import Update, EdgeGroups, DIM
 
 
 class UpdateRunner:
-    def __init__(self, state, update=None, ba_iterations=2, seed=1234):
+    def __init__(self, state, update=None, ba_iterations=2, seed=1234, graph=None):
+        """graph: optional DevicePatchGraph (patchgraph.py).  With it the edge lists and the recurrent state are the
+        store's fixed-capacity arrays: every kernel runs over all `cap` slots, parked slots are dummy edges in groups of
+        their own whose confidence weights are zeroed before bundle adjustment, and a captured CUDA graph of step()
+        stays valid while edges are appended and removed between replays."""
         self.s = state
+        self.pg = graph
         dev = state.poses.device
         if update is None:
             torch.manual_seed(seed)                    # evaluate_tartan.py:173
@@ -33,15 +38,28 @@ class UpdateRunner:
         self.lmbda = torch.as_tensor([1e-4], device=dev)
         self.poses0 = state.poses.clone()
         self.patches0 = state.patches.clone()
-        self.net = torch.zeros(1, state.E, DIM, device=dev, dtype=torch.float32)
         self.timers = None
-        self.corr_buf = torch.zeros(1, state.E, 896, device=dev, dtype=torch.half)   # padding columns stay zero
-        # host-known bounds on the number of groups (no device->host sync in the step)
-        n_live_frames = int((state.kk // self.M).unique().numel())
-        self.max_patch_groups = n_live_frames * self.M
-        self.max_pair_groups = int(torch.unique(state.ii * 100000 + state.jj).numel())
-        self.kk_ring = state.kk % (self.M * self.pmem)
-        self.jj_ring = state.jj % self.mem
+        if graph is None:
+            self.E = state.E
+            self.ii, self.jj, self.kk = state.ii, state.jj, state.kk
+            self.net = torch.zeros(1, state.E, DIM, device=dev, dtype=torch.float32)
+            # host-known bounds on the number of groups (no device->host sync in the step)
+            n_live_frames = int((state.kk // self.M).unique().numel())
+            self.max_patch_groups = n_live_frames * self.M
+            self.max_pair_groups = int(torch.unique(state.ii * 100000 + state.jj).numel())
+            self.kk_ring = state.kk % (self.M * self.pmem)
+            self.jj_ring = state.jj % self.mem
+        else:
+            self.E = graph.cap
+            self.ii, self.jj, self.kk = graph.ii, graph.jj, graph.kk
+            self.net = graph.net                                      # [1, cap, 384] fp32, updated in place
+            # bounds that hold for any topology the store can take: every live patch + the dummy patch; every ordered
+            # frame pair inside the removal window + the dummy pair
+            live = state.cfg["removal"] + 2
+            self.max_patch_groups = min(graph.cap, live * self.M + 1)
+            self.max_pair_groups = min(graph.cap, live * live + 1)
+            self.kk_ring = self.jj_ring = None                       # the ring indices follow the edges: computed per step
+        self.corr_buf = torch.zeros(1, self.E, 896, device=dev, dtype=torch.half)   # padding columns stay zero
 
     def reset(self):
         self.s.poses.copy_(self.poses0)
@@ -55,20 +73,25 @@ class UpdateRunner:
         poses = s.poses.view(1, -1, 7)
         patches = s.patches.view(1, -1, 3, 3, 3)
         intr = s.intrinsics.view(1, -1, 4)
-        coords = pops.transform_fused(poses, patches, intr, s.ii, s.jj, s.kk)               # [1,E,2,3,3]
+        ii, jj, kk = self.ii, self.jj, self.kk
+        kk_ring = self.kk_ring if self.pg is None else kk % (self.M * self.pmem)
+        jj_ring = self.jj_ring if self.pg is None else jj % self.mem
+        coords = pops.transform_fused(poses, patches, intr, ii, jj, kk)               # [1,E,2,3,3]
         if ev is not None:
             ev["corr0"].record()
-        corr = altcorr.corr_pyramid(s.gmap, (s.fmap1, s.fmap2), coords, self.kk_ring, self.jj_ring, 3, 4.0, 896, self.corr_buf)
+        corr = altcorr.corr_pyramid(s.gmap, (s.fmap1, s.fmap2), coords, kk_ring, jj_ring, 3, 4.0, 896, self.corr_buf)
         if ev is not None:
             ev["corr1"].record()
-        groups_kk, groups_ij = EdgeGroups.pair((s.kk, None, s.jj), (s.ii, s.jj, None), self.max_patch_groups, self.max_pair_groups)
+        groups_kk, groups_ij = EdgeGroups.pair((kk, None, jj), (ii, jj, None), self.max_patch_groups, self.max_pair_groups)
         # context gather (dpvo.py:334) and target = centre + delta (dpvo.py:341) are folded into the
         # first LayerNorm pass and the heads kernel
-        self.net, (target, weight, _) = self.update(self.net, s.imap, corr, None, s.ii, s.jj, s.kk, groups_kk, groups_ij,
-                                                    inp_index=self.kk_ring, coords=coords)
+        self.net, (target, weight, _) = self.update(self.net, s.imap, corr, None, ii, jj, kk, groups_kk, groups_ij,
+                                                    inp_index=kk_ring, coords=coords)
+        if self.pg is not None:
+            weight = weight * self.pg.active.view(1, -1, 1)          # parked edges carry no confidence into bundle adjustment
         if ev is not None:
             ev["ba0"].record()
-        fastba.BA_grouped(poses, patches, intr, target, weight, self.lmbda, s.ii, s.jj, s.kk, s.t0, s.n,
+        fastba.BA_grouped(poses, patches, intr, target, weight, self.lmbda, ii, jj, kk, s.t0, s.n,
                           self.ba_iterations, groups_kk, groups_ij)
         if ev is not None:
             ev["ba1"].record()
@@ -157,7 +180,14 @@ class UpdateRunner:
             self.step()
         out_poses.copy_(s.poses[:s.n], non_blocking=True)
         out_depth.copy_(s.patches[:s.n * self.M, 2, 1, 1], non_blocking=True)
-        return h2d, out_poses.numel() * 4 + out_depth.numel() * 4
+        # the results of this frame are on the host once this event has completed: the caller waits for it AFTER
+        # issuing the next frame (two result buffers in rotation), so the device never idles on the host
+        if not hasattr(self, "_ev_done"):
+            self._ev_done, self._ev_i = [torch.cuda.Event(), torch.cuda.Event()], 0
+        ev = self._ev_done[self._ev_i]
+        self._ev_i ^= 1
+        ev.record()
+        return h2d, out_poses.numel() * 4 + out_depth.numel() * 4, ev
 
     def step_e2e(self, hf, out_poses, out_depth):
         """ingest a frame from pinned host memory, update, read poses + patch depths back to host"""

@@ -440,6 +440,32 @@ int64_t dpvo_update_gru_workspace_bytes(void);
 int dpvo_update_gru_heads(float* net32, const void* hij16, const int32_t* group_of, const void* W6, const float* params,
                           const float* coords, int P, float* delta, float* weight, void* workspace, int64_t E, void* stream);
 
+/* ---- Device-resident patch-graph bookkeeping (dpvo_b200/csrc/pgraph.cu) ---------------------------------------------
+ * Fixed-capacity edge arrays ii, jj, kk (int64 [cap]) + active (uint8 [cap]) replace the reference's growing /
+ * shrinking tensors (dpvo/dpvo.py:215-238 append_factors / remove_factors, :282-286 keyframe renumbering) so that a
+ * captured CUDA graph of update() survives topology changes.  A parked slot holds the dummy edge (ii = jj = dummy_frame,
+ * kk = dummy_patch: a reserved frame / patch no real edge uses), so parked edges form their own groups in every
+ * grouping and never mix with real ones; the caller multiplies the confidence weights by `active` before bundle
+ * adjustment.  All decisions read device scalars: no host synchronisation, graph capturable.
+ *   dpvo_pgraph_remove   rule 0: park active edges whose patch frame kk / M < *frame - param          (dpvo.py:300, 306)
+ *                        rule 1: park edges with ii == *frame or jj == *frame, then for the survivors
+ *                                ii > k: kk -= M, ii -= 1;  jj > k: jj -= 1                            (dpvo.py:282-286)
+ *                        enable (device int32, may be NULL): 0 turns the call into a no-op (keyframe decision on device)
+ *   dpvo_pgraph_append   new edges fill the parked slots in index order; state (fp32 [cap, 384] row-major, may be NULL):
+ *                        the rows of the new edges are zeroed (dpvo.py:220-221); slot_of_new (int32 [n_new], required with
+ *                        state) receives the slot of every new edge, -1 if the store is full (*overflow is then set to 1)
+ *   dpvo_pgraph_new_edges  the (2 r - 1) M edges DPVO adds for frame *n - 1 in steady state (n >= r): __edges_forw then
+ *                        __edges_back of dpvo.py:362-375, as (ii = source frame, jj = target frame, kk = patch)
+ * n_active: device int32 running count of active edges (integer atomics).
+ */
+int dpvo_pgraph_remove(int64_t* ii, int64_t* jj, int64_t* kk, uint8_t* active, int64_t cap, int rule,
+                       const int64_t* frame, int64_t param, const int32_t* enable, int64_t dummy_frame,
+                       int64_t dummy_patch, int M, int32_t* n_active, void* stream);
+int dpvo_pgraph_append(int64_t* ii, int64_t* jj, int64_t* kk, uint8_t* active, int64_t cap, const int64_t* new_ii,
+                       const int64_t* new_jj, const int64_t* new_kk, int64_t n_new, const int32_t* enable,
+                       float* state, int32_t* slot_of_new, int32_t* n_active, int32_t* overflow, void* stream);
+int dpvo_pgraph_new_edges(const int64_t* n_dev, int M, int r, int64_t* ii, int64_t* jj, int64_t* kk, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

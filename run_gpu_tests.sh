@@ -4,7 +4,7 @@
 # summarised under profiles/.  Logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-TESTS="${TESTS:-test_chain_gpu test_gemm_gpu test_update_gpu test_graph_gpu test_lie_gpu test_corr_gpu test_ba_gpu test_parity_ref_gpu test_projective_gpu test_step_gpu test_dropin_gpu}"
+TESTS="${TESTS:-test_chain_gpu test_pgraph_gpu test_gemm_gpu test_update_gpu test_graph_gpu test_lie_gpu test_corr_gpu test_ba_gpu test_parity_ref_gpu test_projective_gpu test_step_gpu test_dropin_gpu}"
 for t in $TESTS; do
   if [ -f tests/$t.py ]; then
     timeout -s KILL 600 python -m pytest tests/$t.py -m gpu -q --tb=short -p no:cacheprovider --timeout 300 -s > gpurun_out/$t.log 2>&1
