@@ -86,6 +86,8 @@ struct ChainArgs {
   const int64_t* gidx;         // C: source row per edge, -1 = masked (zero row)
   const __half* hij16;         // G: per-group rows added to the state before the first LayerNorm
   const int32_t* group_of;
+  const __half* hkk16;         // G: a second table of per-group rows (the patch aggregation, net.py:87) and its group ids
+  const int32_t* group_kk;
   const float* coords; int PP; int centre;
   float* delta; float* weight;
   unsigned char* scratch;
@@ -568,8 +570,13 @@ chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           if (ti == 0) prefetch_rows(tile);
           prefetch_rows(tile + gridDim.x);
           const int grp = (live && a.group_of) ? a.group_of[grow] : -1;
+          const int grk = (live && a.group_kk) ? a.group_kk[grow] : -1;
           const __half* hp = a.hij16 + (int64_t)(grp >= 0 ? grp : 0) * CH_DIM + colbase;
-          auto add_h = [&](int c, uint32_t (&v)[32]) { if (grp >= 0) add_half32(v, hp + 32 * c); };
+          const __half* hk = a.hkk16 + (int64_t)(grk >= 0 ? grk : 0) * CH_DIM + colbase;
+          auto add_h = [&](int c, uint32_t (&v)[32]) {
+            if (grk >= 0) add_half32(v, hk + 32 * c);
+            if (grp >= 0) add_half32(v, hp + 32 * c);
+          };
           float sum, sq, mean, rstd;
           ingest_state(m0, nullptr, false, add_h, sum, sq);
           ln_stats(sum, sq, mean, rstd);
@@ -840,12 +847,14 @@ extern "C" int dpvo_update_neighbor_mlp(const void* net16_in, const int64_t* ind
 
 extern "C" int64_t dpvo_update_gru_workspace_bytes(void) { return (int64_t)sm_count() * CH_SCRATCH_PER_CTA; }
 
-extern "C" int dpvo_update_gru_heads(float* net32, const void* hij16, const int32_t* group_of, const void* W6, const float* params,
-                                     const float* coords, int P, float* delta, float* weight, void* workspace, int64_t E, void* stream) {
+extern "C" int dpvo_update_gru_heads(float* net32, const void* hij16, const int32_t* group_of, const void* hkk16, const int32_t* group_kk,
+                                     const void* W6, const float* params, const float* coords, int P, float* delta, float* weight,
+                                     void* workspace, int64_t E, void* stream) {
   DPVO_REQUIRE(E >= 0 && E < (1ll << 31) - CH_M, "update_gru_heads: bad edge count");
   if (E == 0) return DPVO_OK;
   DPVO_REQUIRE(net32 && W6 && params && delta && weight && workspace, "update_gru_heads: null pointer");
-  DPVO_REQUIRE((hij16 == nullptr) == (group_of == nullptr), "update_gru_heads: group rows and group ids come together");
+  DPVO_REQUIRE((hij16 == nullptr) == (group_of == nullptr) && (hkk16 == nullptr) == (group_kk == nullptr), "update_gru_heads: group rows and group ids come together");
+  DPVO_REQUIRE(!hkk16 || al16(hkk16), "update_gru_heads: group rows must be 16-byte aligned");
   DPVO_REQUIRE(al16(net32) && al16(W6) && al16(params) && al16(workspace) && (!hij16 || al16(hij16)) && ((uintptr_t)delta & 7) == 0 && ((uintptr_t)weight & 7) == 0,
                "update_gru_heads: pointers must be 16-byte aligned (delta / weight: 8)");
   DPVO_REQUIRE(!coords || P >= 1, "update_gru_heads: patch size");
@@ -857,7 +866,7 @@ extern "C" int dpvo_update_gru_heads(float* net32, const void* hij16, const int3
   m.X = m.W; m.W0 = m.W; m.Pf = m.W; m.N16 = m.Net;
   ChainArgs a;
   memset(&a, 0, sizeof(a));
-  a.rows = E; a.state = net32; a.p = params; a.n_params = 14 * CH_DIM + 4; a.hij16 = (const __half*)hij16; a.group_of = group_of; a.coords = coords;
+  a.rows = E; a.state = net32; a.p = params; a.n_params = 14 * CH_DIM + 4; a.hij16 = (const __half*)hij16; a.group_of = group_of; a.hkk16 = (const __half*)hkk16; a.group_kk = group_kk; a.coords = coords;
   a.PP = P * P; a.centre = (P / 2) * P + P / 2; a.delta = delta; a.weight = weight; a.scratch = (unsigned char*)workspace;
   return chain_launch<CHAIN_G>(m, a, (cudaStream_t)stream);
 }

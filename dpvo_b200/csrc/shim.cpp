@@ -497,6 +497,23 @@ Tensor residual_add_(Tensor net32, Tensor u, c10::optional<Tensor> group_of, boo
   return n16;
 }
 
+// fp16( net32 + u[group_of] ) without updating net32
+Tensor residual_sum16(Tensor net32, Tensor u, c10::optional<Tensor> group_of) {
+  need_cuda(net32, "net");
+  c10::cuda::CUDAGuard guard(net32.device());
+  TORCH_CHECK(net32.is_contiguous() && net32.scalar_type() == at::kFloat, "residual_sum16: net must be contiguous float32");
+  u = u.contiguous();
+  const int dim = net32.size(-1);
+  const int64_t rows = net32.numel() / dim;
+  Tensor gof;
+  if (group_of.has_value()) { gof = group_of->to(at::kInt).contiguous(); TORCH_CHECK(gof.numel() == rows, "residual_sum16: group_of length"); }
+  else TORCH_CHECK(u.numel() == net32.numel(), "residual_sum16: shape mismatch");
+  Tensor n16 = torch::empty(net32.sizes(), net32.options().dtype(at::kHalf));
+  check(dpvo_residual_sum16(net32.data_ptr(), u.data_ptr(), dt16or32(u), gof.defined() ? gof.data_ptr<int>() : nullptr, n16.data_ptr(), rows, dim, stream()),
+        "dpvo_b200_ext.residual_sum16");
+  return n16;
+}
+
 std::vector<Tensor> gated_residual(Tensor x32, Tensor gate16, Tensor res16, bool want_relu16) {
   need_cuda(x32, "x");
   c10::cuda::CUDAGuard guard(x32.device());
@@ -649,7 +666,7 @@ Tensor update_neighbor_mlp(Tensor net16_in, Tensor index, Tensor Wab, Tensor par
 }
 
 std::vector<Tensor> update_gru_heads(Tensor net32, c10::optional<Tensor> hij16, c10::optional<Tensor> group_of, Tensor W6, Tensor params,
-                                     c10::optional<Tensor> coords, c10::optional<Tensor> workspace) {
+                                     c10::optional<Tensor> coords, c10::optional<Tensor> workspace, c10::optional<Tensor> hkk16, c10::optional<Tensor> group_kk) {
   need_cuda(net32, "net");
   c10::cuda::CUDAGuard guard(net32.device());
   chain_check(net32, at::kFloat, "net32"); chain_check(W6, at::kHalf, "W6"); chain_check(params, at::kFloat, "params");
@@ -662,6 +679,13 @@ std::vector<Tensor> update_gru_heads(Tensor net32, c10::optional<Tensor> hij16, 
     chain_check(hij, at::kHalf, "hij16");
     TORCH_CHECK(hij.size(-1) == 384 && gof.numel() == E, "update_gru_heads: group operand shapes");
   }
+  TORCH_CHECK(hkk16.has_value() == group_kk.has_value(), "update_gru_heads: group rows and group ids come together");
+  Tensor hkk, gkk;
+  if (hkk16.has_value()) {
+    hkk = *hkk16; gkk = group_kk->to(at::kInt).contiguous();
+    chain_check(hkk, at::kHalf, "hkk16");
+    TORCH_CHECK(hkk.size(-1) == 384 && gkk.numel() == E, "update_gru_heads: group operand shapes");
+  }
   Tensor cd; int P = 1;
   if (coords.has_value()) { cd = f32c(*coords); P = cd.size(-1); TORCH_CHECK(cd.numel() == E * 2 * P * P, "update_gru_heads: coords must be [E,2,P,P]"); }
   const int64_t wsb = dpvo_update_gru_workspace_bytes();
@@ -669,7 +693,7 @@ std::vector<Tensor> update_gru_heads(Tensor net32, c10::optional<Tensor> hij16, 
   TORCH_CHECK(ws.is_cuda() && ws.is_contiguous() && (int64_t)(ws.numel() * ws.element_size()) >= wsb, "update_gru_heads: workspace too small");
   Tensor delta = torch::empty({1, E, 2}, net32.options()), weight = torch::empty({1, E, 2}, net32.options());
   check(dpvo_update_gru_heads(net32.data_ptr<float>(), hij.defined() ? hij.data_ptr() : nullptr, gof.defined() ? gof.data_ptr<int>() : nullptr,
-                              W6.data_ptr(), params.data_ptr<float>(), cd.defined() ? cd.data_ptr<float>() : nullptr, P,
+                              hkk.defined() ? hkk.data_ptr() : nullptr, gkk.defined() ? gkk.data_ptr<int>() : nullptr, W6.data_ptr(), params.data_ptr<float>(), cd.defined() ? cd.data_ptr<float>() : nullptr, P,
                               delta.data_ptr<float>(), weight.data_ptr<float>(), ws.data_ptr(), E, stream()),
         "dpvo_b200_ext.update_gru_heads");
   return {delta, weight};
@@ -785,6 +809,7 @@ PYBIND11_MODULE(dpvo_b200_ext, m) {
         py::arg("beta"), py::arg("eps"), py::arg("relu"), py::arg("want32"), py::arg("want16"), py::arg("b_index") = py::none(), py::arg("inplace32") = false, py::arg("c_scale") = py::none());
   m.def("gather_rows_masked", &gather_rows_masked, "masked row gather");
   m.def("residual_add_", &residual_add_, "in-place residual add with optional row indirection");
+  m.def("residual_sum16", &residual_sum16, "fp16(net + u[group]) without updating net", py::arg("net32"), py::arg("u"), py::arg("group_of") = py::none());
   m.def("gated_residual", &gated_residual, "x + sigmoid(g) * r");
   m.def("softagg_reduce", &softagg_reduce, "segment softmax-weighted sum");
   m.def("update_heads", &update_heads, "delta / weight heads (optionally emitting the BA target)", py::arg("net32"), py::arg("W4"),
@@ -797,7 +822,7 @@ PYBIND11_MODULE(dpvo_b200_ext, m) {
   m.def("update_neighbor_mlp", &update_neighbor_mlp, "fused masked neighbour gather + 2-layer MLP + residual (net.py:83-85)", py::arg("net16_in"), py::arg("index"),
         py::arg("Wab"), py::arg("params"), py::arg("net32"), py::arg("net16_out") = py::none());
   m.def("update_gru_heads", &update_gru_heads, "fused group add + GRU + heads (net.py:88-92)", py::arg("net32"), py::arg("hij16"), py::arg("group_of"),
-        py::arg("W6"), py::arg("params"), py::arg("coords") = py::none(), py::arg("workspace") = py::none());
+        py::arg("W6"), py::arg("params"), py::arg("coords") = py::none(), py::arg("workspace") = py::none(), py::arg("hkk16") = py::none(), py::arg("group_kk") = py::none());
   m.def("update_gru_workspace_bytes", &update_gru_workspace_bytes, "scratch bytes of update_gru_heads");
   m.def("pgraph_remove", &pgraph_remove, "park edges by rule on the fixed-capacity edge store", py::arg("ii"), py::arg("jj"), py::arg("kk"), py::arg("active"),
         py::arg("rule"), py::arg("frame"), py::arg("param"), py::arg("enable"), py::arg("dummy_frame"), py::arg("dummy_patch"), py::arg("M"), py::arg("n_active"));

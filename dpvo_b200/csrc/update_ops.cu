@@ -344,16 +344,17 @@ gather_rows_masked_kernel(const void* x, int dx, const int64_t* __restrict__ idx
   }
 }
 
-// net32[r] += u[src(r)]   (src = r, or group_of[r]);  optional fp16 copy of the result
+// net32[r] += u[src(r)]   (src = r, or group_of[r]);  optional fp16 copy of the result.  write_state = false: the sum is only
+// emitted as fp16 (the state stays as it is; the consumer of the state adds u[src] itself)
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 residual_add_kernel(float* net, const void* u, int du, const int32_t* __restrict__ group_of, __half* net16,
-                    int64_t rows, int dim) {
+                    int64_t rows, int dim, bool write_state) {
   const int lane = threadIdx.x & 31;
   for (int64_t r = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * ROW_WARPS) {
     const int64_t src = group_of ? (int64_t)group_of[r] : r;
     for (int col = lane * 4; col < dim; col += 128) {
       const float4 v = add4(load4(net, DPVO_F32, r * dim + col), load4(u, du, src * dim + col));
-      store4(net, DPVO_F32, r * dim + col, v);
+      if (write_state) store4(net, DPVO_F32, r * dim + col, v);
       if (net16) store4(net16, DPVO_F16, r * dim + col, v);
     }
   }
@@ -621,7 +622,17 @@ extern "C" int dpvo_residual_add(void* net32, const void* u, int u_dtype, const 
   DPVO_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0, "residual_add: bad sizes");
   if (rows == 0) return DPVO_OK;
   DPVO_REQUIRE(net32 && u && ok_dt(u_dtype), "residual_add: bad argument");
-  residual_add_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>((float*)net32, u, u_dtype, group_of, (__half*)net16, rows, dim);
+  residual_add_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>((float*)net32, u, u_dtype, group_of, (__half*)net16, rows, dim, true);
+  DPVO_LAUNCH_CHECK("residual_add_kernel");
+  return DPVO_OK;
+}
+
+extern "C" int dpvo_residual_sum16(const void* net32, const void* u, int u_dtype, const int32_t* group_of, void* net16,
+                                   int64_t rows, int dim, void* stream) {
+  DPVO_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0, "residual_sum16: bad sizes");
+  if (rows == 0) return DPVO_OK;
+  DPVO_REQUIRE(net32 && u && net16 && ok_dt(u_dtype), "residual_sum16: bad argument");
+  residual_add_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>((float*)const_cast<void*>(net32), u, u_dtype, group_of, (__half*)net16, rows, dim, false);
   DPVO_LAUNCH_CHECK("residual_add_kernel");
   return DPVO_OK;
 }

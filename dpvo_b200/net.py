@@ -246,8 +246,12 @@ class Update(nn.Module):
         n16b = timed(ex.update_neighbor_mlp, n16, ix, P["C1_W"], P["C1_p"], net32)
         n16 = timed(ex.update_neighbor_mlp, n16b, jx, P["C2_W"], P["C2_p"], net32, n16)
         y = ex.softagg_reduce(L(n16, "fg_kk"), groups_kk.order, groups_kk.group_start, groups_kk.n, groups_kk.max_groups)
-        n16 = ex.residual_add_(net32, L(y, "h_kk"), groups_kk.group_of, True)
+        # net + agg_kk(net) is only needed as the fp16 operand of the next aggregation; the fp32 state itself takes both
+        # aggregation results in the prologue of the GRU chain (net.py:87-88), one pass over the state instead of two
+        h_kk = L(y, "h_kk").reshape(-1, DIM)
+        n16 = ex.residual_sum16(net32, h_kk, groups_kk.group_of)
         y = ex.softagg_reduce(L(n16, "fg_ij"), groups_ij.order, groups_ij.group_start, groups_ij.n, groups_ij.max_groups)
         h_ij = L(y, "h_ij")
-        delta, weight = timed(ex.update_gru_heads, net32, h_ij.reshape(-1, DIM), groups_ij.group_of, P["G_W6"], P["G_p"], self._coords)
+        delta, weight = timed(ex.update_gru_heads, net32, h_ij.reshape(-1, DIM), groups_ij.group_of, P["G_W6"], P["G_p"], self._coords, None,
+                              h_kk, groups_kk.group_of)
         return net32, (delta, weight, None)

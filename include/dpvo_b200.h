@@ -351,6 +351,10 @@ int dpvo_gather_rows_masked(const void* x, int x_dtype, const int64_t* idx,
  */
 int dpvo_residual_add(void* net32, const void* u, int u_dtype, const int32_t* group_of, void* net16,
                       int64_t rows, int dim, void* stream);
+/* net16[e, :] = fp16( net32[e, :] + u[src(e), :] ) without touching net32: the operand of the next dense layer when the
+ * consumer of the fp32 state (dpvo_update_gru_heads) adds u[src] itself -- one pass over the fp32 state less */
+int dpvo_residual_sum16(const void* net32, const void* u, int u_dtype, const int32_t* group_of, void* net16,
+                        int64_t rows, int dim, void* stream);
 
 /* GatedResidual (blocks.py:28-29): y32 = x32 + sigmoid(gate16) * res16; optional relu(y) as fp16. */
 int dpvo_gated_residual(const void* x32, const void* gate16, const void* res16, void* y32, void* y16_relu,
@@ -424,12 +428,14 @@ int dpvo_linear_f16(const void* X, int64_t ldx, const int64_t* gather, const voi
  *     net32 <- net32 + c.2( relu( c.0( mask * net16_in[index] ) ) ),  index[e] = -1 masks the row (mask = 0)
  *     Wab = rows of c.0.weight then c.2.weight [768, 384], params = c.0.bias | c.2.bias.  net16_out != net16_in.
  * dpvo_update_gru_heads  (net.py:88-92, blocks.py:15-29)
- *     x = LN_gru.0( net32 + hij16[group_of[e]] );  y = x + gate1(x) * res1(x);  z = LN_gru.2(y);  net32 <- z + gate2(z) * res2(z)
+ *     x = LN_gru.0( net32 + hkk16[group_kk[e]] + hij16[group_of[e]] );  y = x + gate1(x) * res1(x);  z = LN_gru.2(y);
+ *     net32 <- z + gate2(z) * res2(z)        (net.py:87-88: the two SoftAgg results are added here, not in a pass of their own)
  *     delta = d(net32) (+ centre of coords when given: the BA target of dpvo.py:341), weight = w(net32)
  *     W6 = rows of gru.1.gate.0 | gru.1.res.0 | gru.1.res.2 | gru.3.gate.0 | gru.3.res.0 | gru.3.res.2 weights [2304, 384],
  *     params = gru.0.weight | gru.0.bias | b(gate1) | b(res1.0) | b(res1.2) | gru.2.weight | gru.2.bias | b(gate2) | b(res2.0) |
  *              b(res2.2) | d.1.weight[2,384] | w.1.weight[2,384] | d.1.bias[2] | w.1.bias[2]          (14 x 384 + 4 floats)
- *     hij16 [G, 384] fp16 / group_of int32 [E] may both be NULL (nothing added).  coords [E, 2, P, P] fp32 or NULL.
+ *     hij16 [G, 384] fp16 / group_of int32 [E], hkk16 [G', 384] fp16 / group_kk int32 [E]: each pair may be NULL (nothing
+ *     added).  coords [E, 2, P, P] fp32 or NULL.
  *     delta, weight [E, 2] fp32.  workspace: dpvo_update_gru_workspace_bytes() bytes (row-private scratch, L2 resident).
  */
 int dpvo_update_corr_norm(const void* corr16, int64_t ld_corr, const void* W0, const void* W25, const float* params,
@@ -437,8 +443,9 @@ int dpvo_update_corr_norm(const void* corr16, int64_t ld_corr, const void* W0, c
 int dpvo_update_neighbor_mlp(const void* net16_in, const int64_t* index, const void* Wab, const float* params,
                              float* net32, void* net16_out, int64_t E, void* stream);
 int64_t dpvo_update_gru_workspace_bytes(void);
-int dpvo_update_gru_heads(float* net32, const void* hij16, const int32_t* group_of, const void* W6, const float* params,
-                          const float* coords, int P, float* delta, float* weight, void* workspace, int64_t E, void* stream);
+int dpvo_update_gru_heads(float* net32, const void* hij16, const int32_t* group_of, const void* hkk16, const int32_t* group_kk,
+                          const void* W6, const float* params, const float* coords, int P, float* delta, float* weight,
+                          void* workspace, int64_t E, void* stream);
 
 /* ---- Device-resident patch-graph bookkeeping (dpvo_b200/csrc/pgraph.cu) ---------------------------------------------
  * Fixed-capacity edge arrays ii, jj, kk (int64 [cap]) + active (uint8 [cap]) replace the reference's growing /

@@ -100,7 +100,10 @@ def test_gru_heads_chain(E, with_groups):
     gof = torch.randint(0, G, (E,), generator=g, device="cuda", dtype=torch.int32)
     coords = torch.randn(E, 2, 3, 3, generator=g, device="cuda") * 50
     v = vec.double()
-    x = net.double() + (hij[gof.long()].double() if with_groups else 0)
+    G2 = max(1, E // 22)
+    hkk = torch.randn(G2, DIM, generator=g, device="cuda").half()
+    gkk = torch.randint(0, G2, (E,), generator=g, device="cuda", dtype=torch.int32)
+    x = net.double() + ((hkk[gkk.long()].double() + hij[gof.long()].double()) if with_groups else 0)
     x = _ln(x, v[0], v[1])
     for blk in range(2):
         Wg, Wa, Wb = (w.double() for w in W[3 * blk:3 * blk + 3])
@@ -115,7 +118,7 @@ def test_gru_heads_chain(E, with_groups):
     ref_weight = torch.sigmoid(hd[:, 2:])
     net32 = net.clone()
     delta, weight = ex.update_gru_heads(net32, hij if with_groups else None, gof if with_groups else None, torch.cat(W, 0).contiguous(),
-                                        params, coords)
+                                        params, coords, None, hkk if with_groups else None, gkk if with_groups else None)
     torch.cuda.synchronize()
     _close(net32, x, 3e-3, "state")
     _close(delta.reshape(E, 2) - coords[:, :, 1, 1], ref_delta - coords[:, :, 1, 1].double(), 3e-3, "delta")
