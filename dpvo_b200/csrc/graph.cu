@@ -15,8 +15,8 @@
 namespace dpvo {
 
 constexpr int G_THREADS = 256;
-constexpr int G_ITEMS = 2;
-constexpr int G_TILE = G_THREADS * G_ITEMS;   // 512 edge slots per tile: ~2 x 94 CTAs for the two groupings of an update (the phases are latency bound)
+constexpr int G_ITEMS = 4;
+constexpr int G_TILE = G_THREADS * G_ITEMS;   // 1024 edge slots per tile
 constexpr int G_WARPS = G_THREADS / 32;
 constexpr int G_MAXBITS = 10;                 // radix digit width is chosen per sort, <= 10 bits
 constexpr int G_BINS = 1 << G_MAXBITS;
@@ -36,7 +36,6 @@ struct GroupArgs {
   int32_t* order; int32_t* group_of; int32_t* group_start;
   int64_t* group_key_a; int64_t* group_key_b; int32_t* n_groups;
   GroupHeader* hdr; int32_t* buf0; int32_t* buf1; unsigned* hist; int32_t* tile_sums;
-  unsigned* key32;     // composite key per edge, cached by the first counting pass when it fits 32 bits
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -144,13 +143,7 @@ group_edges_kernel(const GroupArgs a0, const GroupArgs a1) {
   }
   __syncthreads();
 
-  // the composite key of an edge is needed by every pass and by the boundary flags: two or three dependent 8-byte
-  // gathers from the caller's arrays each time.  The first counting pass (identity permutation: coalesced) stores it
-  // as one 32-bit word per edge; everything after reads that word.
-  const bool have_key = composite && (abits + bbits + sbits) <= 32 && (abits + bbits + sbits) > 0;
-  bool key_ready = false;
   auto key_of = [&](int32_t e, int field) -> unsigned long long {
-    if (field == 3 && key_ready) return a.key32[e];
     if (field == 3) {
       unsigned long long k = bias64(a.ka[e]) - amin;
       if (a.kb) k = (k << bbits) | (bias64(a.kb[e]) - bmin);
@@ -179,12 +172,7 @@ group_edges_kernel(const GroupArgs a0, const GroupArgs a1) {
       for (int c = 0; c < G_TILE / G_WARPS / 32; ++c) {
         const int64_t i = base + c * 32 + lane;
         unsigned d = 0xffffffffu;
-        if (i < E) {
-          const int32_t id = src[i];
-          const unsigned long long k = key_of(id, field);
-          if (have_key && !key_ready) a.key32[id] = (unsigned)k;
-          d = (unsigned)(k >> shift) & mask;
-        }
+        if (i < E) d = (unsigned)(key_of(src[i], field) >> shift) & mask;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         if (d != 0xffffffffu && lane == __ffs(peers) - 1) warp_hist[w][d] += __popc(peers);
         __syncwarp();
@@ -204,7 +192,6 @@ group_edges_kernel(const GroupArgs a0, const GroupArgs a1) {
       __syncthreads();
     }
     grid_barrier(&H->barrier, epoch);
-    if (have_key) key_ready = true;                    // written by the counting phase of the first pass, visible after the barrier
 
     // ---- scatter: every block derives the offsets of its own tiles from the tile-major histogram
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
@@ -263,7 +250,6 @@ group_edges_kernel(const GroupArgs a0, const GroupArgs a1) {
   auto is_head = [&](int64_t i) -> int {
     if (i == 0) return 1;
     const int32_t e = src[i], p = src[i - 1];
-    if (key_ready) return (a.key32[e] >> sbits) != (a.key32[p] >> sbits);
     if (a.ka[e] != a.ka[p]) return 1;
     if (a.kb && a.kb[e] != a.kb[p]) return 1;
     return 0;
@@ -334,7 +320,7 @@ static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
 static int64_t group_ws_bytes(int64_t E) {
   const int64_t ntiles = (E + G_TILE - 1) / G_TILE;
-  return align256(sizeof(GroupHeader)) + 3 * align256(E * 4) + align256(ntiles * (int64_t)G_BINS * 4) + align256((ntiles + 1) * 4);
+  return align256(sizeof(GroupHeader)) + 2 * align256(E * 4) + align256(ntiles * (int64_t)G_BINS * 4) + align256((ntiles + 1) * 4);
 }
 
 struct GroupProblem {
@@ -358,8 +344,7 @@ static int group_fill(const GroupProblem& p, GroupArgs& a, cudaStream_t st) {
   a.buf0 = (int32_t*)q; q += align256(E * 4);
   a.buf1 = (int32_t*)q; q += align256(E * 4);
   a.hist = (unsigned*)q; q += align256((int64_t)a.ntiles * G_BINS * 4);
-  a.tile_sums = (int32_t*)q; q += align256((int64_t)(a.ntiles + 1) * 4);
-  a.key32 = (unsigned*)q;
+  a.tile_sums = (int32_t*)q;
   int rc = check_cuda(cudaMemsetAsync(a.hdr, 0, sizeof(GroupHeader), st), "group_edges: memset");
   if (rc) return rc;
   if (E == 0) {

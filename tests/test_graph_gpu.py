@@ -36,6 +36,32 @@ def test_group_edges_random(ext, E):
     _check_group(ext, ka * 100000007, None, sec)      # wide keys: several radix passes
 
 
+@pytest.mark.parametrize("E", [65536, 65537, 150000])
+def test_group_edges_both_kernels_at_the_size_boundary(ext, E):
+    """E <= 65,536 runs inside one thread-block cluster (distributed shared memory), larger graphs on the persistent
+    multi-CTA kernel: same results on either side of the switch"""
+    g = torch.Generator().manual_seed(E)
+    ka = torch.randint(0, 3000, (E,), generator=g)
+    kb = torch.randint(0, 40, (E,), generator=g)
+    sec = torch.randint(0, 40, (E,), generator=g)
+    _check_group(ext, ka, None, sec)
+    _check_group(ext, kb, sec, None)
+
+
+@pytest.mark.parametrize("E", [9, 5000])
+def test_group_edges_keys_wider_than_64_bits(ext, E):
+    """three fields that do not fit one 64-bit composite key: sorted one field at a time"""
+    g = torch.Generator().manual_seed(E)
+    big = 1 << 40
+    ka = torch.randint(-big, big, (E,), generator=g)
+    ka[E // 2:] = ka[:E - E // 2].clone()              # duplicates so that groups have more than one member
+    kb = torch.randint(-big, big, (E,), generator=g)
+    kb[E // 2:] = kb[:E - E // 2].clone()
+    sec = torch.randint(-big, big, (E,), generator=g)
+    _check_group(ext, ka, kb, sec)
+    _check_group(ext, ka, None, sec)
+
+
 def test_group_edges_dpvo_graph(ext):
     ii, jj, kk = synthetic.replay_edges(36, 96, 13, 22)
     _check_group(ext, kk, None, jj)
