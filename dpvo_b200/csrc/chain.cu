@@ -3,7 +3,7 @@
 //
 //   chain A  (net.py:76-77)   net = LN( net + inp[kk] + corr-MLP(corr) )          882->384 ReLU 384 LN ReLU 384
 //   chain C  (net.py:83-85)   net = net + c( mask * net[ix] )                      384 ReLU 384   (c1 and c2)
-//   chain G  (net.py:88-92)   net = GRU( net + h_ij[group] ); delta, weight        LN, gated residual, LN, gated residual, heads
+//   chain G  (net.py:88-92)   net = GRU( net + h_kk[patch] + h_ij[pair] ); delta, weight   LN, gated res., LN, gated res., heads
 //
 // What the separate-layer path paid for and this kernel does not: every intermediate [E,384] activation written to
 // and read back from global memory, one LayerNorm / gating / heads pass over the fp32 state per step, one launch
@@ -13,21 +13,27 @@
 //   warps 0-7  epilogue    TMEM lane quarter = warp % 4 (32 rows), column half = warp / 4 (192 columns).  Bias,
 //                          activation, LayerNorm (row statistics exchanged between the two warps that share a row),
 //                          gating, heads; the fp16 result is written straight into the shared-memory operand tile of
-//                          the NEXT layer in the SWIZZLE_128B K-major layout the UMMA descriptors expect.
+//                          the NEXT layer in the SWIZZLE_128B K-major layout the UMMA descriptors expect.  TMEM loads
+//                          run one 32-column chunk ahead of the arithmetic; all parameters sit in shared memory.
 //   warp  8    MMA issuer  tcgen05.mma.cta_group::1.kind::f16, M=128 N=192 K=16; a layer is 2 column halves x 6
 //                          k-blocks x 4 instructions into a 384-column fp32 accumulator in TMEM
 //   warp  9    W producer  streams the weight k-blocks (192 x 64 fp16 = 24 KB) of every layer of every tile through
-//                          a 4-deep TMA ring; it depends on no data, so it runs ahead across layers and tiles
+//                          a TMA ring (4 deep, 3 in chains A and C); it depends on no data, so it runs ahead across
+//                          layers and tiles
 //   warp 10    (chain A)   streams the 14 k-blocks of the 896-column correlation rows through the operand slots
 //   warps 10-13 (chain C)  gather the neighbour rows net[ix] (masked) into the operand slots with cp.async
 // Shared memory: 6 operand slots of 128 rows x 64 halves (96 KB, one K=384 activation tile, overwritten in place by
-// the layer's own output once its MMAs have retired), the 96 KB weight ring, 4 KB of row-statistics exchange.
-// When a chain is done with its operand tile the slots double as TMA staging for the fp32 state (loads of the
-// residual operand, stores of the new state): each epilogue warp only ever stages in the 12 KB of the slots that
-// hold its own 32 rows x 192 columns, so staging needs no synchronisation between warps.
+// the layer's own output once its MMAs have retired), the weight ring, the parameter vectors, 2-4 KB of exchange.
+// The fp32 recurrent state enters and leaves through TMA boxes of 32 rows x 32 columns (128-byte rows; 64-byte rows
+// halve the achieved rate): loads land in the warp's own 12 KB of the operand slots -- dead once the chain's last MMAs
+// have retired -- so staging needs no synchronisation between warps; chains A and C hand the slots back to their
+// producers as soon as the loads are consumed (the next tile's rows then travel under the rest of the epilogue) and
+// stage their stores in 6 KB of dedicated memory per warp.  The un-normalised values of a LayerNorm wait in TMEM
+// (tcgen05.st) between the statistics pass and the normalisation pass.
 // Row-private intermediates of chain G (the sigmoid gate, the fp32 LayerNorm output that the gated residual adds
 // to) live in a per-CTA global scratch laid out chunk-major ([16-byte chunk][row]), so that the row-per-thread
-// ownership TMEM imposes gives perfectly coalesced 512-byte accesses; it is rewritten every tile and stays in L2.
+// ownership TMEM imposes gives perfectly coalesced 512-byte accesses; it is rewritten every tile and stays in L2
+// (TMEM is full: 384 accumulator columns of 512).  Measured timelines and what bounds each phase: DESIGN.md 3.1, 5.2.
 #include "common.cuh"
 #include "tc.cuh"
 #include <cuda.h>
@@ -738,9 +744,14 @@ typedef CUresult (*ChEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 static int ch_tmap(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elt, int64_t rows, int64_t cols, int64_t ld,
                    int box_cols, int box_rows, CUtensorMapSwizzle sw) {
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+  // the encoder is a driver symbol, the same for every device of the process: looked up once (thread-safe static init)
+  static void* const p = []() -> void* {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return f;
+  }();
+  if (!p) {
     set_error("update chain: cuTensorMapEncodeTiled is not available from the driver");
     return DPVO_ERR_CUDA;
   }
