@@ -166,8 +166,12 @@ ba_reduce_kernel(const BaArgs a) {
       if (lane == 0) { a.Qk[g] = qk; a.uk[g] = usum; }
       if constexpr (SYSTEM) {
         // S -= Q_k E_k E_k^T (upper triangle), y -= Q_k u_k E_k: lanes stride the columns of a row; rows are independent
-        // read-modify-writes of disjoint addresses, unrolled so that their shared-memory latencies overlap
+        // read-modify-writes of disjoint addresses, unrolled so that their shared-memory latencies overlap.  A patch that
+        // touches no free pose (all of a long video but its last window) has a zero row and nothing to add.
         __syncwarp();
+        bool nz = false;
+        for (int c = lane; c < N6; c += 32) nz |= ek[c] != 0.0f;
+        if (__any_sync(0xffffffffu, nz)) {
         int base = 0;
 #pragma unroll 4
         for (int r = 0; r < N6; ++r) {
@@ -177,6 +181,7 @@ ba_reduce_kernel(const BaArgs a) {
           base += N6 - r;
         }
         for (int c = lane; c < N6; c += 32) Sw[base + c] -= qk * usum * ek[c];
+        }
       }
       __syncwarp();
     } else {

