@@ -428,7 +428,7 @@ def run_ours(args):
                         "traffic": ncu.get("gemm_dram_bytes"), "peak_source": which + ", sustained dense 16-bit (kernels timed inside a step)",
                         "algorithmic_flop_per_step": gemm_flop, "kernel_ms": gemm_ms,
                         "timing": "sum of CUDA-event intervals around each of the launches, eager pass, same stream; since round 2 the intervals also contain the LayerNorm, gating, residual and heads work that is fused into the chain kernels' epilogues",
-                        "traffic_note": "sum of dram__bytes_read+write over the dense-layer launches of one update, ncu capture under profiles/ (null until captured for this build)"},
+                        "traffic_note": "sum of dram__bytes_read+write over the 8 dense-layer launches of one update, ncu --set full capture of this build: profiles/r02_ncu_gemm_step.json"},
            "roofline_corr": {"kernel": "corr_fwd_tc (2-level patch correlation, tcgen05 + TMA)", "kernel_ms": corr_ms,
                              "algorithmic_bytes_per_launch": BYTES_PER_EDGE_FP16 * E, "algorithmic_GBps": corr_alg,
                              "note": "SURVEY 8(d)'s per-edge window bytes are served by L2 (each frame is reused ~11x), so algorithmic/HBM-peak (%.2f) is "
