@@ -55,7 +55,7 @@ constexpr int chain_threads(int chain) { return chain == CHAIN_C ? 320 + CH_GATH
 struct ChainBars {
   uint64_t w_full[4], w_empty[4];
   uint64_t a_full[CH_KB], a_empty[CH_KB];
-  uint64_t acc_full, epi_done, slots_free;
+  uint64_t acc_full[2], epi_done, slots_free;     // acc_full[h]: the MMAs of column half h of a layer have retired
   uint64_t stg[CH_EPI_WARPS][6];
   uint32_t tmem_base;
 };
@@ -113,6 +113,15 @@ struct ChainArgs {
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // one MUFU op instead of two (the gate layers evaluate 49k sigmoids per tile and the SFU does 16 per clock):
 // sigmoid(x) = 0.5 + 0.5 tanh(x / 2), tanh.approx has a relative error of 2^-11; the result is rounded to fp16 anyway
+// two gates per SFU op: the pre-activations are rounded to fp16 first (which is where the reference's autocast computes
+// its sigmoid, blocks.py:19 under dpvo.py:332), tanh.approx.f16x2 has an absolute error of 2^-11, the gate is stored as fp16
+__device__ __forceinline__ __half2 sigmoid_tanh_h2(float a, float b) {
+  const __half2 x = __floats2half2_rn(0.5f * a, 0.5f * b);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&x)));
+  const __half2 half = __float2half2_rn(0.5f);
+  return __hfma2(*reinterpret_cast<const __half2*>(&t), half, half);
+}
 __device__ __forceinline__ float sigmoid_tanh(float x) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
@@ -141,7 +150,8 @@ chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     if ((smem_u32(ch_smem) & 1023u) != 0) { printf("chain_kernel: shared memory base is not 1024-byte aligned\n"); __trap(); }
     for (int s = 0; s < CH_WST; ++s) { mbar_init(&bars->w_full[s], 1); mbar_init(&bars->w_empty[s], 1); }
     for (int s = 0; s < CH_KB; ++s) { mbar_init(&bars->a_full[s], CHAIN == CHAIN_C ? CH_GATHER_THREADS : 1); mbar_init(&bars->a_empty[s], 1); }
-    mbar_init(&bars->acc_full, 1);
+    mbar_init(&bars->acc_full[0], 1);
+    mbar_init(&bars->acc_full[1], 1);
     mbar_init(&bars->epi_done, CH_EPI_WARPS);
     mbar_init(&bars->slots_free, CH_EPI_WARPS);
     for (int w = 0; w < CH_EPI_WARPS; ++w) for (int j = 0; j < 6; ++j) mbar_init(&bars->stg[w][j], 1);
@@ -247,10 +257,11 @@ chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     };
     auto chained_layer = [&]() {                                     // operand = the six slots, in place
       CH_STAMP(ti, m_l, 0);
-      for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h) {
         for (int kb = 0; kb < CH_KB; ++kb) issue(smem_u32(slots + kb * CH_SLOT), h, kb == 0);
-      if (lane == 0) tc_commit(&bars->acc_full);
-      __syncwarp();
+        if (lane == 0) tc_commit(&bars->acc_full[h]);                // half h complete: an epilogue that does not touch the
+        __syncwarp();                                                // operand slots may start on it while the other half runs
+      }
       CH_STAMP(ti, m_l, 1);
       ++m_l;
     };
@@ -266,7 +277,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           if (lane == 0) tc_commit(&bars->a_empty[s]);
           __syncwarp();
         }
-        if (lane == 0) tc_commit(&bars->acc_full);
+        if (lane == 0) { tc_commit(&bars->acc_full[0]); tc_commit(&bars->acc_full[1]); }
         __syncwarp();
         CH_STAMP(ti, m_l, 1);
         ++m_l;
@@ -279,7 +290,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             if (h == 0) mbar_wait_bounded(&bars->a_full[kb], ti & 1);
             issue(smem_u32(slots + kb * CH_SLOT), h, kb == 0);
           }
-        if (lane == 0) tc_commit(&bars->acc_full);
+        if (lane == 0) { tc_commit(&bars->acc_full[0]); tc_commit(&bars->acc_full[1]); }
         __syncwarp();
         CH_STAMP(ti, m_l, 1);
         ++m_l;
@@ -304,7 +315,25 @@ chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     // parameter vectors: shared-memory copy (index in units of 384 floats, see the launchers for the order)
     auto SP = [&](int vec) { return sparam + (vec * CH_DIM - Cfg::PARAM_SKIP); };
 
-    auto wait_acc = [&]() { mbar_wait_bounded(&bars->acc_full, acc_n & 1); ++acc_n; tc_fence_after(); if (warp == 0) CH_STAMP(e_ti, e_l, 2); };
+    auto wait_acc = [&]() {                                          // both halves of the layer have retired
+      mbar_wait_bounded(&bars->acc_full[0], acc_n & 1);
+      mbar_wait_bounded(&bars->acc_full[1], acc_n & 1);
+      ++acc_n; tc_fence_after();
+      if (warp == 0) CH_STAMP(e_ti, e_l, 2);
+    };
+    // for an epilogue that only reads its own accumulator half and writes nothing the MMAs read: the warps of half 0 start
+    // as soon as their half has retired (the second half is still being multiplied) and catch up with the second barrier
+    // before they report the epilogue done -- every warp passes every phase of both barriers, in order
+    auto wait_acc_own_half = [&]() {
+      mbar_wait_bounded(&bars->acc_full[0], acc_n & 1);
+      if (h == 1) mbar_wait_bounded(&bars->acc_full[1], acc_n & 1);
+      tc_fence_after();
+      if (warp == 0) CH_STAMP(e_ti, e_l, 2);
+    };
+    auto wait_acc_other_half = [&]() {
+      if (h == 0) mbar_wait_bounded(&bars->acc_full[1], acc_n & 1);
+      ++acc_n;
+    };
     auto epi_arrive = [&]() {                                        // TMEM reads done, operand tile written
       fence_proxy_async();
       tc_fence_before();
@@ -607,19 +636,20 @@ chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         for (int blk = 0; blk < 2; ++blk) {
           const int pv = 2 + 5 * blk;                                // bg | ba | bb | (g | be of the LayerNorm that follows block 0)
           {                                                          // gate = sigmoid(x Wg + bg) -> scratch
-            wait_acc();
+            wait_acc_own_half();
             for_chunks32([&](int c, uint32_t (&r)[32]) {
               add_vec32(r, SP(pv) + colbase + 32 * c);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 uint4 o;
-                *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(sigmoid_tanh(__uint_as_float(r[8 * i])), sigmoid_tanh(__uint_as_float(r[8 * i + 1])));
-                *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(sigmoid_tanh(__uint_as_float(r[8 * i + 2])), sigmoid_tanh(__uint_as_float(r[8 * i + 3])));
-                *reinterpret_cast<__half2*>(&o.z) = __floats2half2_rn(sigmoid_tanh(__uint_as_float(r[8 * i + 4])), sigmoid_tanh(__uint_as_float(r[8 * i + 5])));
-                *reinterpret_cast<__half2*>(&o.w) = __floats2half2_rn(sigmoid_tanh(__uint_as_float(r[8 * i + 6])), sigmoid_tanh(__uint_as_float(r[8 * i + 7])));
+                *reinterpret_cast<__half2*>(&o.x) = sigmoid_tanh_h2(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1]));
+                *reinterpret_cast<__half2*>(&o.y) = sigmoid_tanh_h2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
+                *reinterpret_cast<__half2*>(&o.z) = sigmoid_tanh_h2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
+                *reinterpret_cast<__half2*>(&o.w) = sigmoid_tanh_h2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
                 __stcg(gate_ptr(4 * c + i), o);
               }
             });
+            wait_acc_other_half();
             epi_arrive();
           }
           epi_relu_act(SP(pv + 1));                                  // r1 = relu(x Wa + ba) -> operand tile (x is not needed as an operand again)
