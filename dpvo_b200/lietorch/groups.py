@@ -229,6 +229,11 @@ class RxSO3(LieGroup):
     group_name, group_id, manifold_dim, embedded_dim = "RxSO3", 2, 4, 5
     id_elem = torch.tensor([0.0, 0.0, 0.0, 1.0, 1.0])
 
+    def __init__(self, data):
+        if isinstance(data, Sim3):                       # rotation + scale part of a similarity (groups.py:259-262)
+            data = data.data[..., 3:8]
+        super().__init__(data)
+
 
 class SE3(LieGroup):
     group_name, group_id, manifold_dim, embedded_dim = "SE3", 3, 6, 7
@@ -247,6 +252,17 @@ class SE3(LieGroup):
 class Sim3(LieGroup):
     group_name, group_id, manifold_dim, embedded_dim = "Sim3", 4, 7, 8
     id_elem = torch.tensor([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0])
+
+    def __init__(self, data):
+        # embeddings of the smaller groups (groups.py:297-311): unit scale, and zero translation for a pure rotation
+        if isinstance(data, SO3):
+            q = data.data
+            data = torch.cat([torch.zeros_like(q[..., :3]), q, torch.ones_like(q[..., :1])], -1)
+        elif isinstance(data, SE3):
+            data = torch.cat([data.data, torch.ones_like(data.data[..., :1])], -1)
+        elif isinstance(data, Sim3):
+            data = data.data
+        super().__init__(data)
 
 
 class LieGroupParameter(torch.Tensor):
