@@ -543,7 +543,7 @@ Tensor softagg_reduce(Tensor fg, Tensor order, Tensor group_start, Tensor n_grou
               "softagg_reduce: group_start must be int32 with at least max_groups + 1 entries");
   TORCH_CHECK(n_groups.is_cuda() && n_groups.scalar_type() == at::kInt && n_groups.numel() == 1, "softagg_reduce: n_groups must be a device int32 scalar");
   TORCH_CHECK(max_groups >= 0 && max_groups <= E, "softagg_reduce: max_groups must be in [0, E]");
-  Tensor y = torch::zeros({1, max_groups, dim}, fg.options());
+  Tensor y = torch::empty({1, max_groups, dim}, fg.options());   // rows past the group count are zeroed by the kernel itself
   const at::Half* base = fg.data_ptr<at::Half>();
   check(dpvo_softagg_reduce(base, base + dim, 2 * dim, order.data_ptr<int>(), group_start.data_ptr<int>(),
                             n_groups.data_ptr<int>(), max_groups, y.data_ptr(), dim, stream()),

@@ -454,6 +454,10 @@ softagg_reduce_kernel(const __half* __restrict__ f, const __half* __restrict__ g
       __syncthreads();
     }
   }
+  // y holds max_groups rows (a host-side bound): the rows past the true group count are defined (zero) as well, so that
+  // the dense layer that follows reads no uninitialised memory and the caller needs no separate fill
+  for (int g = G + blockIdx.x; g < max_groups; g += gridDim.x)
+    for (int c = threadIdx.x * 2; c < dim; c += blockDim.x * 2) *reinterpret_cast<__half2*>(y + (int64_t)g * dim + c) = __float2half2_rn(0.f);
 }
 
 // ---- heads: out[r] = (Wd relu(net[r]) + bd, sigmoid(Ww relu(net[r]) + bw)) ---------------------
