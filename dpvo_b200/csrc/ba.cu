@@ -326,23 +326,35 @@ ba_solve_kernel(const BaArgs a) {
     // adds them in CTA order, one entry per thread, 32 loads in flight, and deposits the sums in CTA 0's shared memory.
     SolveSmem* root = cluster.map_shared_rank(&sm, 0);
     const int n_ent = ba_packed_entries(N6), n_tri = N6 * (N6 + 1) / 2;
-    for (int e = rank * BA_SOLVE_THREADS + tid; e < n_ent; e += BA_CLUSTER * BA_SOLVE_THREADS) {
-      int row = N6, col = e - n_tri;                              // gradient entries follow the packed triangle
-      if (e < n_tri) {
-        int rem = e;
-        row = 0;
-        while (rem >= N6 - row) { rem -= N6 - row; ++row; }
-        col = row + rem;
-      }
+    // two adjacent lanes per entry: the even lane adds the first half of the partial systems, the odd lane the second half
+    // (both in CTA order), one shuffle joins them -- half the dependent-load rounds of one thread per entry
+    const int half_parts = (a.n_part + 1) / 2;
+    const int limit = ((2 * n_ent + 31) / 32) * 32;               // warp-uniform loop bound (the shuffle needs every lane)
+    for (int idx = rank * BA_SOLVE_THREADS + tid; idx < limit; idx += BA_CLUSTER * BA_SOLVE_THREADS) {
+      const int e = idx >> 1, hf = idx & 1;
+      const bool valid = e < n_ent;
+      const int cb = hf ? half_parts : 0, ce = hf ? a.n_part : half_parts;
       float s = 0.0f;
-      for (int c0 = 0; c0 < a.n_part; c0 += 32) {
-        float v[32];
+      if (valid) {
+        for (int c0 = cb; c0 < ce; c0 += 32) {
+          float v[32];
 #pragma unroll
-        for (int u = 0; u < 32; ++u) v[u] = (c0 + u < a.n_part) ? __ldcg(a.part + (int64_t)(c0 + u) * n_ent + e) : 0.0f;
+          for (int u = 0; u < 32; ++u) v[u] = (c0 + u < ce) ? __ldcg(a.part + (int64_t)(c0 + u) * n_ent + e) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 32; ++u) s += v[u];
+          for (int u = 0; u < 32; ++u) s += v[u];
+        }
       }
-      root->S[row][col] = s;
+      const float other = __shfl_xor_sync(0xffffffffu, s, 1);
+      if (valid && hf == 0) {
+        int row = N6, col = e - n_tri;                              // gradient entries follow the packed triangle
+        if (e < n_tri) {
+          int rem = e;
+          row = 0;
+          while (rem >= N6 - row) { rem -= N6 - row; ++row; }
+          col = row + rem;
+        }
+        root->S[row][col] = s + other;
+      }
     }
     BA_STAMP(1);
   } else if (N > 0) {
